@@ -1,0 +1,171 @@
+"""CPU: the oracle restatement against the reference's own outputs (tests/golden/reference_golden.pt,
+made by tests/golden/make_golden.py from the reference function bodies) and against closed-form
+identities / known values of the restated DDIM scheduler."""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import standins
+from oracle import ddim, energy, guidance, prototypes
+
+GUIDE_CASES = ["guidance_small", "guidance_d2048", "guidance_b1"]
+
+
+def _nets(case):
+    unet, vae, enc = standins.make_nets(seed=0, feat_dim=case["feat_dim"])
+    unet.load_state_dict(case["unet"]); vae.load_state_dict(case["vae"]); enc.load_state_dict(case["enc"])
+    return unet, vae, enc
+
+
+def _args(case):
+    return types.SimpleNamespace(**case["args"])
+
+
+def test_alpha_bar_known_values():
+    ab = ddim.alphas_cumprod()
+    assert ab.dtype == torch.float32 and ab.shape == (1000,)
+    for t, v in [(981, 0.0057755), (481, 0.3022954), (1, 0.9982960), (0, 0.9991500)]:
+        assert abs(float(ab[t]) - v) < 5e-7, (t, float(ab[t]))
+
+
+def test_timesteps_and_index_arithmetic():
+    ts = ddim.timesteps(50)
+    assert ts[0] == 981 and ts[-1] == 1 and len(ts) == 50 and int(ts[30]) == 381
+    assert [ddim.start_index(s) for s in (0.9, 0.8, 0.5, 1.0)] == [4, 9, 25, 0]
+    assert ddim.guide_timesteps(ts, 20, 2) == [381, 361]
+    assert ddim.guide_timesteps(ts, 50, 50) == ts.tolist()
+    a_t, a_prev = ddim.alpha_pair(1)
+    assert float(a_prev) == float(ddim.alphas_cumprod()[0])  # set_alpha_to_one=False
+
+
+def test_split_mask_reference_semantics():
+    assert ddim.split_mask(10, 0, 4) == [0, 1, 2]
+    assert ddim.split_mask(10, 3, 4) == [9]
+    assert ddim.split_mask(8, 1, 2) == [4, 5, 6, 7]
+    assert sorted(sum((ddim.split_mask(101, s, 8) for s in range(8)), [])) == list(range(101))
+
+
+def test_ddim_identities():
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 4, 8, 8, generator=g); n = torch.randn(2, 4, 8, 8, generator=g)
+    a_t, a_prev = ddim.alpha_pair(481)
+    noisy = ddim.add_noise(x, n, a_t)
+    prev, x0 = ddim.ddim_step(n, noisy, a_t, a_prev)
+    assert torch.allclose(x0, x, atol=2e-5)                                  # true noise -> x0 reconstructs x
+    assert torch.allclose(prev, ddim.add_noise(x, n, a_prev), atol=2e-5)     # eta=0 -> same noise at prev t
+
+
+@pytest.mark.parametrize("name", GUIDE_CASES)
+def test_denoise_one_step_vs_reference(golden, name):
+    case = golden[name]; unet, vae, enc = _nets(case); args = _args(case)
+    sched = ddim.OracleDDIMScheduler(50)
+    with torch.no_grad():
+        prev, x0 = guidance.denoise_one_step(args, case["latents"], sched, case["denoise"]["t"], unet,
+                                             case["prompt_embeds"], None)
+    assert torch.equal(prev, case["denoise"]["prev"]) and torch.equal(x0, case["denoise"]["x0"])
+    a_t, a_prev = ddim.alpha_pair(case["denoise"]["t"])
+    p2, x2 = ddim.cfg_ddim_step(case["denoise"]["noise_pred"], case["latents"], args.guidance_scale, a_t, a_prev)
+    assert torch.equal(p2, prev) and torch.equal(x2, x0)
+
+
+@pytest.mark.parametrize("name", GUIDE_CASES)
+def test_transform_guidance_vs_reference(golden, name):
+    case = golden[name]; unet, vae, enc = _nets(case); args = _args(case)
+    sched = ddim.OracleDDIMScheduler(50); proc = standins.IdentityProcessor()
+    for key, gp, lp in [("transform", case["global_proto"], case["local_proto"]),
+                        ("transform_global_only", case["global_proto"], None)]:
+        torch.manual_seed(case[key]["seed"])
+        lat, score = guidance.transform_guidance(args, case["latents"].clone(), {"targets": case["targets"]},
+                                                 [381, 361], sched, unet, case["prompt_embeds"], None, vae, enc, proc,
+                                                 torch.float32, None, gp, lp)
+        assert torch.allclose(lat, case[key]["latents_out"], rtol=0, atol=1e-6)
+        assert abs(float(score) - case[key]["score"]) < 1e-6
+
+
+@pytest.mark.parametrize("name", GUIDE_CASES)
+def test_direct_guidance_vs_reference(golden, name):
+    case = golden[name]; unet, vae, enc = _nets(case); args = _args(case)
+    sched = ddim.OracleDDIMScheduler(50); proc = standins.IdentityProcessor()
+    for key, gp, lp in [("direct", case["global_proto"], case["local_proto"]),
+                        ("direct_local_only", None, case["local_proto"])]:
+        lat, x0, score = guidance.direct_guidance(args, case["latents"].clone(), {"targets": case["targets"]}, 381,
+                                                  sched, unet, case["prompt_embeds"], None, vae, enc, proc,
+                                                  torch.float32, None, gp, lp)
+        assert torch.allclose(lat, case[key]["latents_out"], rtol=0, atol=1e-6)
+        assert torch.equal(x0, case[key]["x0"])
+        assert abs(float(score) - case[key]["score"]) < 1e-6
+
+
+def test_linfball_vs_reference(golden):
+    c = golden["linfball"]
+    out = guidance.linfball_proj(c["center"].clone(), c["radius"], c["t"].clone())
+    assert torch.equal(out, c["out"])
+    # closed form used by the CUDA kernel == the reference's masked assignment
+    y = torch.maximum(torch.minimum(c["t"], c["center"] + c["radius"]), c["center"] - c["radius"])
+    assert torch.equal(y, c["out"])
+
+
+@pytest.mark.parametrize("normalize_f", [False, True])
+@pytest.mark.parametrize("use", [(True, True), (True, False), (False, True)])
+def test_energy_closed_form_vs_autograd(normalize_f, use):
+    g = torch.Generator().manual_seed(3)
+    B, C, K, D = 5, 7, 3, 96
+    f = torch.randn(B, D, generator=g, dtype=torch.float64, requires_grad=True)
+    gp = torch.nn.functional.normalize(torch.randn(C, D, generator=g, dtype=torch.float64), dim=-1)
+    lp = torch.nn.functional.normalize(torch.randn(C, K, D, generator=g, dtype=torch.float64), dim=-1)
+    y = torch.randint(0, C, (B,), generator=g).tolist()
+    G = gp if use[0] else None
+    L = lp if use[1] else None
+    score = energy.energy_score(f, y, G, L, 0.7, 1.3, normalize_f=normalize_f)
+    (grad,) = torch.autograd.grad(score, f)
+    s2, per, kstar, g2 = energy.energy_fwd_bwd(f.detach().numpy(), y, None if G is None else G.numpy(),
+                                               None if L is None else L.numpy(), 0.7, 1.3, normalize_f=normalize_f)
+    assert abs(float(score) - float(s2)) < 1e-12
+    assert np.allclose(grad.numpy(), g2, rtol=1e-10, atol=1e-13)
+
+
+def test_energy_zero_distance_subgradient():
+    gp = torch.nn.functional.normalize(torch.randn(3, 16, dtype=torch.float64), dim=-1)
+    f = gp[[1, 2]].clone().requires_grad_(True)       # f == its class prototype -> ||.|| = 0 -> grad 0
+    score = energy.energy_score(f, [1, 2], gp, None, 1.0, 1.0)
+    (grad,) = torch.autograd.grad(score, f)
+    assert torch.count_nonzero(grad) == 0
+    _, _, _, g2 = energy.energy_fwd_bwd(f.detach().numpy(), [1, 2], gp.numpy(), None, 1.0, 1.0)
+    assert np.count_nonzero(g2) == 0
+
+
+@pytest.mark.parametrize("name", ["proto_caltech_like", "proto_d2048", "proto_k5"])
+def test_prototypes_vs_reference(golden, name):
+    c = golden[name]
+    fn = prototypes.l2_normalize_rows(c["features"].numpy())
+    gl, lc, labels = prototypes.extract_prototype_from_features(fn, c["labels"].tolist(), c["K"])
+    assert np.array_equal(gl, c["global_prototypes"].numpy())
+    assert np.array_equal(lc, c["local_prototypes"].numpy())
+    # from-scratch UPGMA restatement == sklearn labels, class by class
+    cw = prototypes.class_wise(fn, c["labels"].tolist())
+    for ci, (Xc, lab) in enumerate(zip(cw, labels)):
+        Xc = np.stack(Xc)
+        mine = prototypes.upgma_labels(Xc, c["K"])
+        assert np.array_equal(mine, lab)
+        assert np.array_equal(prototypes.cluster_means(Xc, mine, c["K"]), lc[ci])
+
+
+def test_agglomerative_error_cases():
+    X = prototypes.l2_normalize_rows(np.random.default_rng(0).normal(size=(2, 8)).astype(np.float32))
+    with pytest.raises(ValueError):
+        prototypes.upgma_labels(X[:1], 1)
+    with pytest.raises(ValueError):
+        prototypes.upgma_labels(X, 3)
+
+
+def test_kmeans_spec_matches_sklearn_lloyd():
+    from sklearn.cluster import KMeans
+    rng = np.random.default_rng(5)
+    centers = rng.normal(size=(4, 32)) * 3
+    X = prototypes.l2_normalize_rows((centers[rng.integers(0, 4, 200)] + rng.normal(size=(200, 32))).astype(np.float32))
+    mu, assign = prototypes.kmeans_class(X, 4, iters=30)
+    km = KMeans(n_clusters=4, init=prototypes.kmeans_init(X, 4), n_init=1, algorithm="lloyd", tol=0, max_iter=30).fit(X)
+    assert np.array_equal(km.labels_, assign)
+    assert np.allclose(km.cluster_centers_, mu, rtol=1e-5, atol=1e-7)

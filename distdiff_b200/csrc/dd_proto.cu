@@ -1,0 +1,644 @@
+// K1 (row L2-normalise + class gather + class sums), K2 (class means), K3 (k-means assign + accumulate).
+//
+// Layout in HBM: features are kept CLASS-SORTED ([N,D] fp32, rows of one class contiguous, dataset order
+// inside a class; class_off[C+1] are the offsets).  K1 produces that layout directly from the raw
+// features (a row gather through the label sort permutation), so the per-class structure every later
+// stage needs (class means, k-means, agglomerative) costs no extra pass.
+//
+// Both streaming kernels are persistent: grid = #SMs, CTA g owns the contiguous row range
+// [N*g/G, N*(g+1)/G) (perfect balance, every row read from HBM exactly once) and walks it in batches of
+// R rows that never straddle a class.  Rows are staged global->shared by the TMA engine
+// (cp.async.bulk, completion on an mbarrier) through a multi-stage ring, so the SM always has
+// (stages-1)*R*D*4 bytes of loads in flight with zero register cost.  Inside a batch every thread OWNS
+// 8 columns (two float4) of D: the class's K centroids for those columns live in registers, the K dot
+// products per row are finished with a transposed warp-shuffle reduction + one shared-memory hop across
+// the 8 warps, and the per-cluster sums for the thread's columns are accumulated in registers -- no
+// atomics anywhere.  At a class boundary each CTA stores its partial sums to workspace slot (g + c)
+// (unique because both the CTA ranges and the classes are ordered); a second small kernel adds the slots
+// of a class in fixed order -> bit-reproducible fp64 sums, ready for the NCCL all-reduce.
+//
+// HBM roofline: N*D*4 bytes read per pass (+ N*D*4 written by K1 for the sorted copy); the centroid table
+// (C*K*D*4 <= 8 MB) and the partial slots stay in the 126 MB L2.
+#include "dd_common.cuh"
+
+namespace dd {
+
+constexpr int PK_THREADS = 256;
+constexpr int PK_WARPS = PK_THREADS / 32;
+constexpr int PK_CH = 2;          // float4 chunks owned per thread -> D <= 2048
+constexpr int PK_MAX_D = PK_THREADS * PK_CH * 4;
+constexpr int PK_MAX_STAGES = 12;
+constexpr size_t PK_RING_BYTES = 192 * 1024;
+
+__host__ __device__ constexpr int pow2_ge(int v) { return v <= 1 ? 1 : v <= 2 ? 2 : v <= 4 ? 4 : v <= 8 ? 8 : v <= 16 ? 16 : 32; }
+__host__ __device__ constexpr int log2i(int v) { return v <= 1 ? 0 : 1 + log2i(v / 2); }
+
+// Transposed warp reduction: every lane holds P partial values; afterwards lane L holds, in v[0], the
+// warp-wide sum of value index (L >> (5 - log2 P)).  Costs ~P shuffles instead of 5*P.
+template <int P, int OFF>
+__device__ __forceinline__ void xreduce(float (&v)[32], int lane) {
+    if constexpr (P > 1) {
+        const bool up = (lane & OFF) != 0;
+#pragma unroll
+        for (int i = 0; i < P / 2; ++i) {
+            const float keep = up ? v[i + P / 2] : v[i];
+            const float send = up ? v[i] : v[i + P / 2];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
+        }
+        xreduce<P / 2, OFF / 2>(v, lane);
+    } else if constexpr (OFF >= 1) {
+        v[0] += __shfl_xor_sync(0xffffffffu, v[0], OFF);
+        xreduce<1, OFF / 2>(v, lane);
+    }
+}
+
+__device__ __forceinline__ float dot4(const float4& a, const float4& b, float acc) {
+    float2 s = ffma2(make_float2(a.x, a.y), make_float2(b.x, b.y), make_float2(acc, 0.f));
+    s = ffma2(make_float2(a.z, a.w), make_float2(b.z, b.w), s);
+    return s.x + s.y;
+}
+
+// largest c with off[c] <= row  (=> off[c+1] > row because off[C] = N > row)
+__device__ __forceinline__ int find_class(const int64_t* __restrict__ off, int C, int64_t row) {
+    int lo = 0, hi = C;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(off + mid) <= row) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// next batch of <= R rows of a single class, starting at the cursor
+__device__ __forceinline__ void take_batch(const int64_t* __restrict__ off, int64_t r1, int R, int64_t& row, int& c,
+                                           int64_t& b_row, int& b_n, int& b_c) {
+    int64_t end = __ldg(off + c + 1);
+    while (end <= row) { ++c; end = __ldg(off + c + 1); }
+    int64_t n = end - row;
+    if (n > R) n = R;
+    if (n > r1 - row) n = r1 - row;
+    b_row = row; b_n = (int)n; b_c = c;
+    row += n;
+}
+
+__device__ __forceinline__ void store_f64x4(double* dst, double a, double b, double c, double d) {
+    reinterpret_cast<double2*>(dst)[0] = make_double2(a, b);
+    reinterpret_cast<double2*>(dst)[1] = make_double2(c, d);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K3: assign + accumulate
+// ---------------------------------------------------------------------------------------------------
+template <int K, int R, typename AccT>
+__global__ void __launch_bounds__(PK_THREADS, 1)
+kmeans_stream_kernel(const float* __restrict__ x, const int64_t* __restrict__ class_off, int64_t N, int D, int C,
+                     const float* __restrict__ centroid, const float* __restrict__ cnorm, int32_t* __restrict__ assign,
+                     double* __restrict__ ws_sum, int64_t* __restrict__ ws_cnt, double* __restrict__ ws_inertia,
+                     int stages) {
+    constexpr int V = R * (K + 1);      // per row: K dots + ||x||^2
+    constexpr int P = pow2_ge(V);
+    static_assert(V <= 32, "R*(K+1) must fit one warp");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const size_t stage_elems = (size_t)R * D;
+    float* ring = reinterpret_cast<float*>(smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)stages * stage_elems * sizeof(float));
+    float* red = reinterpret_cast<float*>(full + PK_MAX_STAGES);  // [2][PK_WARPS][32]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int G = gridDim.x, g = blockIdx.x;
+    const int64_t r0 = N * g / G, r1 = N * (g + 1) / G;
+    const int nch = D >> 2;
+    int chunk[PK_CH];
+    bool own[PK_CH];
+#pragma unroll
+    for (int ch = 0; ch < PK_CH; ++ch) { chunk[ch] = tid + ch * PK_THREADS; own[ch] = chunk[ch] < nch; }
+
+    if (tid == 0) {
+        for (int s = 0; s < stages; ++s) mbar_init(&full[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    int64_t irow = r0, crow = r0;
+    int ic = (r0 < r1) ? find_class(class_off, C, r0) : 0;
+    int cc = ic;
+    if (tid == 0) {
+        for (int s = 0; s < stages && irow < r1; ++s) {
+            int64_t br; int bn, bc;
+            take_batch(class_off, r1, R, irow, ic, br, bn, bc);
+            const uint32_t bytes = (uint32_t)bn * D * sizeof(float);
+            mbar_expect_tx(&full[s], bytes);
+            bulk_g2s(ring + (size_t)s * stage_elems, x + br * D, bytes, &full[s]);
+        }
+    }
+
+    float4 mu[K][PK_CH];
+    AccT acc[K][PK_CH][4];
+    float cn[K];
+    int cnt[K];
+    double inert = 0.0;
+    int cur = -1;
+
+    auto flush = [&](int c) {
+        const int64_t slot = (int64_t)g + c;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+#pragma unroll
+            for (int ch = 0; ch < PK_CH; ++ch)
+                if (own[ch])
+                    store_f64x4(ws_sum + (slot * K + k) * D + chunk[ch] * 4, (double)acc[k][ch][0], (double)acc[k][ch][1],
+                                (double)acc[k][ch][2], (double)acc[k][ch][3]);
+            if (tid == 0) ws_cnt[slot * K + k] = cnt[k];
+        }
+    };
+
+    int it = 0, buf = 0;
+    while (crow < r1) {
+        int64_t brow; int bn, bc;
+        take_batch(class_off, r1, R, crow, cc, brow, bn, bc);
+        if (bc != cur) {
+            if (cur >= 0) flush(cur);
+            cur = bc;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const float4* crow4 = reinterpret_cast<const float4*>(centroid + ((int64_t)bc * K + k) * D);
+#pragma unroll
+                for (int ch = 0; ch < PK_CH; ++ch) {
+                    mu[k][ch] = own[ch] ? __ldg(crow4 + chunk[ch]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    acc[k][ch][0] = acc[k][ch][1] = acc[k][ch][2] = acc[k][ch][3] = (AccT)0;
+                }
+                cn[k] = __ldg(cnorm + (int64_t)bc * K + k);
+                cnt[k] = 0;
+            }
+        }
+        const int s = it % stages;
+        mbar_wait(&full[s], (uint32_t)((it / stages) & 1));
+
+        const float* st = ring + (size_t)s * stage_elems;
+        float4 xv[R][PK_CH];
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int ch = 0; ch < PK_CH; ++ch)
+                xv[r][ch] = own[ch] ? *reinterpret_cast<const float4*>(st + (size_t)r * D + chunk[ch] * 4)
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = 0.f;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                float a = 0.f;
+#pragma unroll
+                for (int ch = 0; ch < PK_CH; ++ch) a = dot4(xv[r][ch], mu[k][ch], a);
+                v[r * (K + 1) + k] = a;
+            }
+            float a = 0.f;
+#pragma unroll
+            for (int ch = 0; ch < PK_CH; ++ch) a = dot4(xv[r][ch], xv[r][ch], a);
+            v[r * (K + 1) + K] = a;
+        }
+        xreduce<P, 16>(v, lane);
+        if ((lane & (32 / P - 1)) == 0) red[(buf * PK_WARPS + warp) * 32 + (lane >> (5 - log2i(P)))] = v[0];
+        __syncthreads();
+        // stage s has been read into registers by everybody: refill it
+        if (tid == 0 && irow < r1) {
+            int64_t br; int bn2, bc2;
+            take_batch(class_off, r1, R, irow, ic, br, bn2, bc2);
+            const uint32_t bytes = (uint32_t)bn2 * D * sizeof(float);
+            mbar_expect_tx(&full[s], bytes);
+            bulk_g2s(ring + (size_t)s * stage_elems, x + br * D, bytes, &full[s]);
+        }
+        float tot = 0.f;
+        if (lane < V) {
+#pragma unroll
+            for (int w = 0; w < PK_WARPS; ++w) tot += red[(buf * PK_WARPS + w) * 32 + lane];  // fixed order
+        }
+        // lane r < R: argmin_k (cnorm_k - 2 <x_r, mu_k>), lowest k on ties
+        float best = INFINITY, xn = 0.f;
+        int bestk = 0;
+        const int rbase = (lane < R ? lane : 0) * (K + 1);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const float d = __shfl_sync(0xffffffffu, tot, rbase + k);
+            const float sc = fmaf(-2.f, d, cn[k]);
+            if (sc < best) { best = sc; bestk = k; }
+        }
+        xn = __shfl_sync(0xffffffffu, tot, rbase + K);
+        const float d2 = fmaxf(xn + best, 0.f);
+        if (warp == 0 && lane < bn) assign[brow + lane] = bestk;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int kr = __shfl_sync(0xffffffffu, bestk, r);
+            const float dr = __shfl_sync(0xffffffffu, d2, r);
+            if (r < bn) {
+                inert += (double)dr;
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    if (kr == k) {  // CTA-uniform
+                        ++cnt[k];
+#pragma unroll
+                        for (int ch = 0; ch < PK_CH; ++ch) {
+                            acc[k][ch][0] += (AccT)xv[r][ch].x; acc[k][ch][1] += (AccT)xv[r][ch].y;
+                            acc[k][ch][2] += (AccT)xv[r][ch].z; acc[k][ch][3] += (AccT)xv[r][ch].w;
+                        }
+                    }
+                }
+            }
+        }
+        buf ^= 1;
+        ++it;
+    }
+    if (cur >= 0) flush(cur);
+    if (tid == 0) ws_inertia[g] = inert;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K1: gather by perm, L2-normalise, write class-sorted copy, per-class partial sums
+// ---------------------------------------------------------------------------------------------------
+template <int R>
+__global__ void __launch_bounds__(PK_THREADS, 1)
+rownorm_stream_kernel(const float* __restrict__ feat, const int64_t* __restrict__ perm, const int64_t* __restrict__ class_off,
+                      int64_t N, int D, int C, float* __restrict__ feat_sorted, double* __restrict__ ws_sum,
+                      int64_t* __restrict__ ws_cnt, int stages) {
+    constexpr int P = pow2_ge(R);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const size_t stage_elems = (size_t)R * D;
+    float* ring = reinterpret_cast<float*>(smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)stages * stage_elems * sizeof(float));
+    float* red = reinterpret_cast<float*>(full + PK_MAX_STAGES);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int G = gridDim.x, g = blockIdx.x;
+    const int64_t r0 = N * g / G, r1 = N * (g + 1) / G;
+    const int nch = D >> 2;
+    int chunk[PK_CH];
+    bool own[PK_CH];
+#pragma unroll
+    for (int ch = 0; ch < PK_CH; ++ch) { chunk[ch] = tid + ch * PK_THREADS; own[ch] = chunk[ch] < nch; }
+
+    if (tid == 0) {
+        for (int s = 0; s < stages; ++s) mbar_init(&full[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](int s, int64_t br, int bn) {
+        const uint32_t row_bytes = (uint32_t)D * sizeof(float);
+        mbar_expect_tx(&full[s], row_bytes * bn);
+        for (int i = 0; i < bn; ++i) {
+            const int64_t src = perm ? __ldg(perm + br + i) : br + i;
+            bulk_g2s(ring + (size_t)s * stage_elems + (size_t)i * D, feat + src * D, row_bytes, &full[s]);
+        }
+    };
+
+    int64_t irow = r0, crow = r0;
+    int ic = (r0 < r1) ? find_class(class_off, C, r0) : 0;
+    int cc = ic;
+    if (tid == 0) {
+        for (int s = 0; s < stages && irow < r1; ++s) {
+            int64_t br; int bn, bc;
+            take_batch(class_off, r1, R, irow, ic, br, bn, bc);
+            issue(s, br, bn);
+        }
+    }
+
+    double acc[PK_CH][4];
+    int cnt = 0, cur = -1;
+    auto flush = [&](int c) {
+        const int64_t slot = (int64_t)g + c;
+#pragma unroll
+        for (int ch = 0; ch < PK_CH; ++ch)
+            if (own[ch]) store_f64x4(ws_sum + slot * D + chunk[ch] * 4, acc[ch][0], acc[ch][1], acc[ch][2], acc[ch][3]);
+        if (tid == 0) ws_cnt[slot] = cnt;
+    };
+
+    int it = 0, buf = 0;
+    while (crow < r1) {
+        int64_t brow; int bn, bc;
+        take_batch(class_off, r1, R, crow, cc, brow, bn, bc);
+        if (bc != cur) {
+            if (cur >= 0) flush(cur);
+            cur = bc;
+            cnt = 0;
+#pragma unroll
+            for (int ch = 0; ch < PK_CH; ++ch) acc[ch][0] = acc[ch][1] = acc[ch][2] = acc[ch][3] = 0.0;
+        }
+        const int s = it % stages;
+        mbar_wait(&full[s], (uint32_t)((it / stages) & 1));
+        const float* st = ring + (size_t)s * stage_elems;
+        float4 xv[R][PK_CH];
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = 0.f;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            float a = 0.f;
+#pragma unroll
+            for (int ch = 0; ch < PK_CH; ++ch) {
+                xv[r][ch] = own[ch] ? *reinterpret_cast<const float4*>(st + (size_t)r * D + chunk[ch] * 4)
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+                a = dot4(xv[r][ch], xv[r][ch], a);
+            }
+            v[r] = a;
+        }
+        xreduce<P, 16>(v, lane);
+        if ((lane & (32 / P - 1)) == 0) red[(buf * PK_WARPS + warp) * 32 + (lane >> (5 - log2i(P)))] = v[0];
+        __syncthreads();
+        if (tid == 0 && irow < r1) {
+            int64_t br; int bn2, bc2;
+            take_batch(class_off, r1, R, irow, ic, br, bn2, bc2);
+            issue(s, br, bn2);
+        }
+        float tot = 0.f;
+        if (lane < R) {
+#pragma unroll
+            for (int w = 0; w < PK_WARPS; ++w) tot += red[(buf * PK_WARPS + w) * 32 + lane];
+        }
+        const float nrm_l = sqrtf(tot);  // f.norm(dim=-1)  (dataloader.py:677)
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const float nrm = __shfl_sync(0xffffffffu, nrm_l, r);
+            if (r < bn) {
+#pragma unroll
+                for (int ch = 0; ch < PK_CH; ++ch) {
+                    if (own[ch]) {
+                        float4 o;
+                        o.x = __fdiv_rn(xv[r][ch].x, nrm); o.y = __fdiv_rn(xv[r][ch].y, nrm);
+                        o.z = __fdiv_rn(xv[r][ch].z, nrm); o.w = __fdiv_rn(xv[r][ch].w, nrm);
+                        *reinterpret_cast<float4*>(feat_sorted + (brow + r) * D + chunk[ch] * 4) = o;
+                        acc[ch][0] += (double)o.x; acc[ch][1] += (double)o.y;
+                        acc[ch][2] += (double)o.z; acc[ch][3] += (double)o.w;
+                    }
+                }
+            }
+        }
+        cnt += bn;
+        buf ^= 1;
+        ++it;
+    }
+    if (cur >= 0) flush(cur);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// fixed-order reduction of the per-(CTA, class) partial slots  ->  sum [C,K,D] f64, cnt [C,K] i64
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(PK_THREADS)
+partial_reduce_kernel(const double* __restrict__ ws_sum, const int64_t* __restrict__ ws_cnt,
+                      const double* __restrict__ ws_inertia, const int64_t* __restrict__ class_off, int64_t N, int D, int C,
+                      int K, int G, double* __restrict__ sum, int64_t* __restrict__ cnt, double* __restrict__ inertia) {
+    const int c = blockIdx.x / K, k = blockIdx.x % K;
+    const int64_t lo = class_off[c], hi = class_off[c + 1];
+    int g_lo = 0, g_hi = -1;
+    if (hi > lo) {  // CTA owning row r: g(r) = floor(((r+1)*G - 1) / N)
+        g_lo = (int)(((lo + 1) * G - 1) / N);
+        g_hi = (int)((hi * G - 1) / N);
+    }
+    for (int col = threadIdx.x; col < D; col += PK_THREADS) {
+        double s = 0.0;
+        for (int g = g_lo; g <= g_hi; ++g) s += ws_sum[(((int64_t)g + c) * K + k) * D + col];
+        sum[((int64_t)c * K + k) * D + col] = s;
+    }
+    if (threadIdx.x == 0) {
+        int64_t n = 0;
+        for (int g = g_lo; g <= g_hi; ++g) n += ws_cnt[((int64_t)g + c) * K + k];
+        cnt[(int64_t)c * K + k] = n;
+        if (blockIdx.x == 0 && inertia) {
+            double t = 0.0;
+            for (int g = 0; g < G; ++g) t += ws_inertia[g];
+            *inertia = t;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K2 and small row kernels (one CTA per row; tables are C*K rows -- tiny)
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double block_sum_f64(double v, double* sh) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) sh[w] = v;
+    __syncthreads();
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < PK_WARPS; ++i) t += sh[i];
+    return t;
+}
+
+__global__ void __launch_bounds__(PK_THREADS)
+class_mean_kernel(const double* __restrict__ sum, const int64_t* __restrict__ cnt, int D, float* __restrict__ mean,
+                  float* __restrict__ mean_unit) {
+    __shared__ double sh[PK_WARPS];
+    const int64_t r = blockIdx.x;
+    const int64_t n = cnt[r];
+    double sq = 0.0;
+    for (int col = threadIdx.x; col < D; col += PK_THREADS) {
+        const float m = n > 0 ? (float)(sum[r * D + col] / (double)n) : 0.f;
+        if (mean) mean[r * D + col] = m;
+        sq += (double)m * (double)m;
+    }
+    if (!mean_unit) return;
+    const float nrm = (float)sqrt(block_sum_f64(sq, sh));
+    for (int col = threadIdx.x; col < D; col += PK_THREADS) {
+        const float m = n > 0 ? (float)(sum[r * D + col] / (double)n) : 0.f;
+        mean_unit[r * D + col] = __fdiv_rn(m, nrm);
+    }
+}
+
+__global__ void __launch_bounds__(PK_THREADS)
+normalize_rows_kernel(const float* __restrict__ in, int D, float* __restrict__ out) {
+    __shared__ double sh[PK_WARPS];
+    const int64_t r = blockIdx.x;
+    double sq = 0.0;
+    for (int col = threadIdx.x; col < D; col += PK_THREADS) { const float m = in[r * D + col]; sq += (double)m * (double)m; }
+    const float nrm = (float)sqrt(block_sum_f64(sq, sh));
+    for (int col = threadIdx.x; col < D; col += PK_THREADS) out[r * D + col] = __fdiv_rn(in[r * D + col], nrm);
+}
+
+__global__ void __launch_bounds__(PK_THREADS)
+kmeans_seed_kernel(const float* __restrict__ x, const int64_t* __restrict__ row_idx, int D, double* __restrict__ sum,
+                   int64_t* __restrict__ cnt) {
+    const int64_t r = blockIdx.x;
+    const int64_t src = row_idx[r];
+    for (int col = threadIdx.x; col < D; col += PK_THREADS) sum[r * D + col] = src >= 0 ? (double)x[src * D + col] : 0.0;
+    if (threadIdx.x == 0) cnt[r] = src >= 0 ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(PK_THREADS)
+kmeans_update_kernel(const double* __restrict__ sum, const int64_t* __restrict__ cnt, int D, float* __restrict__ centroid,
+                     float* __restrict__ cnorm) {
+    __shared__ double sh[PK_WARPS];
+    const int64_t r = blockIdx.x;
+    const int64_t n = cnt[r];
+    double sq = 0.0;
+    for (int col = threadIdx.x; col < D; col += PK_THREADS) {
+        float m;
+        if (n > 0) {
+            m = (float)(sum[r * D + col] / (double)n);
+            centroid[r * D + col] = m;
+        } else {
+            m = centroid[r * D + col];  // an empty cluster keeps its centroid
+        }
+        sq += (double)m * (double)m;
+    }
+    const double t = block_sum_f64(sq, sh);
+    if (threadIdx.x == 0) cnorm[r] = (float)t;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+struct WsLayout {
+    size_t sum_off, cnt_off, inertia_off, total;
+};
+static WsLayout ws_layout(int D, int C, int K, int G) {
+    WsLayout w;
+    const size_t slots = (size_t)G + (size_t)C;
+    w.sum_off = 0;
+    w.cnt_off = slots * K * D * sizeof(double);
+    w.inertia_off = w.cnt_off + slots * K * sizeof(int64_t);
+    w.total = w.inertia_off + (size_t)G * sizeof(double);
+    return w;
+}
+
+static int pick_stages(int R, int D) {
+    const size_t stage = (size_t)R * D * sizeof(float);
+    int s = (int)(PK_RING_BYTES / stage);
+    if (s > PK_MAX_STAGES) s = PK_MAX_STAGES;
+    return s;
+}
+static size_t smem_bytes(int stages, int R, int D) {
+    return (size_t)stages * R * D * sizeof(float) + PK_MAX_STAGES * sizeof(uint64_t) + 2 * PK_WARPS * 32 * sizeof(float);
+}
+
+template <int K, int R, typename AccT>
+static int launch_kmeans(const float* x, const int64_t* class_off, int64_t N, int D, int C, const float* centroid,
+                         const float* cnorm, int32_t* assign, double* ws_sum, int64_t* ws_cnt, double* ws_inertia, int G,
+                         cudaStream_t st) {
+    const int stages = pick_stages(R, D);
+    DD_REQUIRE(stages >= 2, DD_EUNSUPPORTED, "kmeans: D=%d too large for the shared-memory ring", D);
+    const size_t smem = smem_bytes(stages, R, D);
+    auto kern = kmeans_stream_kernel<K, R, AccT>;
+    DD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<G, PK_THREADS, smem, st>>>(x, class_off, N, D, C, centroid, cnorm, assign, ws_sum, ws_cnt, ws_inertia, stages);
+    DD_LAUNCH_OK();
+    return 0;
+}
+
+}  // namespace dd
+
+extern "C" {
+
+size_t dd_proto_workspace_bytes(int D, int C, int K) {
+    if (D <= 0 || C <= 0 || K <= 0) return 0;
+    return dd::ws_layout(D, C, K, dd::sm_count()).total;
+}
+
+int dd_rownorm_classsum(const float* feat, const int64_t* perm, const int64_t* class_off, int64_t N, int D, int C,
+                        float* feat_sorted, double* class_sum, int64_t* class_cnt, void* ws, size_t ws_bytes,
+                        dd_stream_t stream) {
+    DD_REQUIRE(feat && class_off && feat_sorted && class_sum && class_cnt && ws, DD_EINVAL, "dd_rownorm_classsum: null pointer");
+    DD_REQUIRE(N >= 0 && D >= 4 && C >= 1, DD_EINVAL, "dd_rownorm_classsum: bad sizes N=%lld D=%d C=%d", (long long)N, D, C);
+    DD_REQUIRE(D % 4 == 0 && D <= dd::PK_MAX_D, DD_EUNSUPPORTED, "dd_rownorm_classsum: D=%d must be a multiple of 4 and <= %d", D,
+               dd::PK_MAX_D);
+    DD_REQUIRE(dd::aligned16(feat) && dd::aligned16(feat_sorted) && dd::aligned16(ws), DD_EINVAL,
+               "dd_rownorm_classsum: feat / feat_sorted / ws must be 16-byte aligned");
+    const int G = dd::sm_count();
+    const dd::WsLayout w = dd::ws_layout(D, C, 1, G);
+    DD_REQUIRE(ws_bytes >= w.total, DD_EWORKSPACE, "dd_rownorm_classsum: workspace %zu < %zu bytes", ws_bytes, w.total);
+    cudaStream_t st = (cudaStream_t)stream;
+    double* ws_sum = (double*)((char*)ws + w.sum_off);
+    int64_t* ws_cnt = (int64_t*)((char*)ws + w.cnt_off);
+    constexpr int R = 4;
+    const int stages = dd::pick_stages(R, D);
+    const size_t smem = dd::smem_bytes(stages, R, D);
+    auto kern = dd::rownorm_stream_kernel<R>;
+    DD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (N > 0) {
+        kern<<<G, dd::PK_THREADS, smem, st>>>(feat, perm, class_off, N, D, C, feat_sorted, ws_sum, ws_cnt, stages);
+        DD_LAUNCH_OK();
+    }
+    dd::partial_reduce_kernel<<<C, dd::PK_THREADS, 0, st>>>(ws_sum, ws_cnt, nullptr, class_off, N > 0 ? N : 1, D, C, 1, G,
+                                                           class_sum, class_cnt, nullptr);
+    DD_LAUNCH_OK();
+    return 0;
+}
+
+int dd_class_mean(const double* sum, const int64_t* cnt, int64_t R, int D, float* mean, float* mean_unit, dd_stream_t stream) {
+    DD_REQUIRE(sum && cnt && (mean || mean_unit), DD_EINVAL, "dd_class_mean: null pointer");
+    DD_REQUIRE(R >= 0 && D >= 1, DD_EINVAL, "dd_class_mean: bad sizes");
+    if (R == 0) return 0;
+    dd::class_mean_kernel<<<(unsigned)R, dd::PK_THREADS, 0, (cudaStream_t)stream>>>(sum, cnt, D, mean, mean_unit);
+    DD_LAUNCH_OK();
+    return 0;
+}
+
+int dd_normalize_rows(const float* in, int64_t R, int D, float* out, dd_stream_t stream) {
+    DD_REQUIRE(in && out && R >= 0 && D >= 1, DD_EINVAL, "dd_normalize_rows: bad arguments");
+    if (R == 0) return 0;
+    dd::normalize_rows_kernel<<<(unsigned)R, dd::PK_THREADS, 0, (cudaStream_t)stream>>>(in, D, out);
+    DD_LAUNCH_OK();
+    return 0;
+}
+
+int dd_kmeans_seed(const float* x_sorted, const int64_t* row_idx, int64_t R, int D, double* sum, int64_t* cnt,
+                   dd_stream_t stream) {
+    DD_REQUIRE(x_sorted && row_idx && sum && cnt && R >= 0 && D >= 1, DD_EINVAL, "dd_kmeans_seed: bad arguments");
+    if (R == 0) return 0;
+    dd::kmeans_seed_kernel<<<(unsigned)R, dd::PK_THREADS, 0, (cudaStream_t)stream>>>(x_sorted, row_idx, D, sum, cnt);
+    DD_LAUNCH_OK();
+    return 0;
+}
+
+int dd_kmeans_update(const double* sum, const int64_t* cnt, int C, int K, int D, float* centroid, float* cnorm,
+                     dd_stream_t stream) {
+    DD_REQUIRE(sum && cnt && centroid && cnorm && C >= 1 && K >= 1 && D >= 1, DD_EINVAL, "dd_kmeans_update: bad arguments");
+    dd::kmeans_update_kernel<<<(unsigned)(C * K), dd::PK_THREADS, 0, (cudaStream_t)stream>>>(sum, cnt, D, centroid, cnorm);
+    DD_LAUNCH_OK();
+    return 0;
+}
+
+int dd_kmeans_assign_accum(const float* x_sorted, const int64_t* class_off, int64_t N, int D, int C, int K,
+                           const float* centroid, const float* cnorm, int32_t* assign, double* sum, int64_t* cnt,
+                           double* inertia, void* ws, size_t ws_bytes, dd_stream_t stream) {
+    DD_REQUIRE(x_sorted && class_off && centroid && cnorm && assign && sum && cnt && ws, DD_EINVAL,
+               "dd_kmeans_assign_accum: null pointer");
+    DD_REQUIRE(N >= 0 && D >= 4 && C >= 1, DD_EINVAL, "dd_kmeans_assign_accum: bad sizes N=%lld D=%d C=%d", (long long)N, D, C);
+    DD_REQUIRE(K >= 1 && K <= 15, DD_EUNSUPPORTED, "dd_kmeans_assign_accum: K=%d outside 1..15", K);
+    DD_REQUIRE(D % 4 == 0 && D <= dd::PK_MAX_D, DD_EUNSUPPORTED,
+               "dd_kmeans_assign_accum: D=%d must be a multiple of 4 and <= %d", D, dd::PK_MAX_D);
+    DD_REQUIRE(dd::aligned16(x_sorted) && dd::aligned16(centroid) && dd::aligned16(ws), DD_EINVAL,
+               "dd_kmeans_assign_accum: x_sorted / centroid / ws must be 16-byte aligned");
+    const int G = dd::sm_count();
+    const dd::WsLayout w = dd::ws_layout(D, C, K, G);
+    DD_REQUIRE(ws_bytes >= w.total, DD_EWORKSPACE, "dd_kmeans_assign_accum: workspace %zu < %zu bytes", ws_bytes, w.total);
+    cudaStream_t st = (cudaStream_t)stream;
+    double* ws_sum = (double*)((char*)ws + w.sum_off);
+    int64_t* ws_cnt = (int64_t*)((char*)ws + w.cnt_off);
+    double* ws_in = (double*)((char*)ws + w.inertia_off);
+    int rc = 0;
+    if (N > 0) {
+#define DD_KM(KK, RR, ACC) \
+    case KK: rc = dd::launch_kmeans<KK, RR, ACC>(x_sorted, class_off, N, D, C, centroid, cnorm, assign, ws_sum, ws_cnt, ws_in, G, st); break;
+        switch (K) {
+            DD_KM(1, 8, double) DD_KM(2, 8, double) DD_KM(3, 8, double)
+            DD_KM(4, 4, double) DD_KM(5, 4, double)
+            DD_KM(6, 4, float) DD_KM(7, 4, float)
+            DD_KM(8, 2, float) DD_KM(9, 2, float) DD_KM(10, 2, float) DD_KM(11, 2, float) DD_KM(12, 2, float)
+            DD_KM(13, 2, float) DD_KM(14, 2, float) DD_KM(15, 2, float)
+        }
+#undef DD_KM
+        if (rc) return rc;
+    } else {
+        DD_CUDA_OK(cudaMemsetAsync(ws_in, 0, (size_t)G * sizeof(double), st));
+    }
+    dd::partial_reduce_kernel<<<C * K, dd::PK_THREADS, 0, st>>>(ws_sum, ws_cnt, ws_in, class_off, N > 0 ? N : 1, D, C, K, G, sum,
+                                                               cnt, inertia);
+    DD_LAUNCH_OK();
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,420 @@
+"""Torch-tensor front end of the C ABI (include/distdiff_sm100.h).
+
+PyTorch is used for device memory, streams and autograd bookkeeping only; every arithmetic op on the
+hot path is a kernel of libdistdiff_sm100.so.  No CPU path: CPU tensors raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import DistDiffError, check
+
+_DTYPES = {torch.float32: _lib.DD_F32, torch.float16: _lib.DD_F16, torch.bfloat16: _lib.DD_BF16}
+
+# launches of OUR kernels since process start (bench.py reports the delta over the timed region)
+launch_count = 0
+
+
+def _count(n: int = 1) -> None:
+    global launch_count
+    launch_count += n
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _req(t: torch.Tensor, name: str, dtype=None) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise DistDiffError(f"{name}: expected a tensor")
+    if not t.is_cuda:
+        raise DistDiffError(f"{name}: CUDA tensor required (the guidance hot path has no CPU fallback)")
+    if dtype is not None and t.dtype != dtype:
+        raise DistDiffError(f"{name}: expected {dtype}, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _code(t: torch.Tensor) -> int:
+    try:
+        return _DTYPES[t.dtype]
+    except KeyError:
+        raise DistDiffError(f"unsupported latent dtype {t.dtype} (f32 / f16 / bf16)") from None
+
+
+# ------------------------------------------------------------------------------------------------
+# K5  CFG + DDIM step
+# ------------------------------------------------------------------------------------------------
+def _split_noise(noise_pred: torch.Tensor, x: torch.Tensor, cfg: bool):
+    noise_pred = _req(noise_pred, "noise_pred", x.dtype)
+    n = x.numel()
+    if cfg:
+        if noise_pred.numel() != 2 * n:
+            raise DistDiffError(f"noise_pred has {noise_pred.numel()} elements, expected 2 x {n} (CFG batch)")
+        es = noise_pred.element_size()
+        return noise_pred, C.c_void_p(noise_pred.data_ptr()), C.c_void_p(noise_pred.data_ptr() + n * es)
+    if noise_pred.numel() != n:
+        raise DistDiffError(f"noise_pred has {noise_pred.numel()} elements, expected {n}")
+    return noise_pred, C.c_void_p(noise_pred.data_ptr()), None
+
+
+def cfg_ddim_step(noise_pred: torch.Tensor, x: torch.Tensor, guidance_scale: float, a_t: float, a_prev: float,
+                  cfg: bool = True, grad: Optional[torch.Tensor] = None, rho: float = 0.0,
+                  want_prev: bool = True, want_x0: bool = True):
+    """No-grad fused step.  noise_pred: [2B,...] (uncond first, text second) when ``cfg`` else [B,...].
+    Returns (x_prev, x0); entries not wanted are None.  generate_data.py:115-120 (+ :762 with grad/rho)."""
+    x = _req(x, "latents")
+    keep, pu, pt = _split_noise(noise_pred, x, cfg)
+    if grad is not None:
+        grad = _req(grad, "grad", x.dtype)
+    x_prev = torch.empty_like(x) if want_prev else None
+    x0 = torch.empty_like(x) if want_x0 else None
+    check(_lib.lib().dd_cfg_ddim_fwd(pu, pt, _ptr(x), x.numel(), _code(x), float(guidance_scale), float(a_t),
+                                     float(a_prev), _ptr(grad), float(rho), _ptr(x_prev), _ptr(x0), _stream()),
+          "dd_cfg_ddim_fwd")
+    _count()
+    del keep
+    return x_prev, x0
+
+
+class CfgDdimStep(torch.autograd.Function):
+    """Differentiable K5: (noise_pred[2B], x) -> (x_prev, x0).  Backward is one dd_cfg_ddim_bwd launch."""
+
+    @staticmethod
+    def forward(ctx, noise_pred, x, guidance_scale, a_t, a_prev, cfg):
+        x_prev, x0 = cfg_ddim_step(noise_pred.detach(), x.detach(), guidance_scale, a_t, a_prev, cfg)
+        ctx.consts = (float(guidance_scale), float(a_t), float(a_prev), bool(cfg))
+        ctx.meta = (noise_pred.shape, x.shape, x.dtype)
+        return x_prev, x0
+
+    @staticmethod
+    def backward(ctx, g_prev, g_x0):
+        s, a_t, a_prev, cfg = ctx.consts
+        np_shape, x_shape, dtype = ctx.meta
+        need_np, need_x = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if g_prev is None and g_x0 is None:
+            return None, None, None, None, None, None
+        ref = g_prev if g_prev is not None else g_x0
+        g_prev = None if g_prev is None else _req(g_prev, "g_prev", dtype)
+        g_x0 = None if g_x0 is None else _req(g_x0, "g_x0", dtype)
+        n = ref.numel()
+        g_np = torch.empty(np_shape, dtype=dtype, device=ref.device) if need_np else None
+        g_x = torch.empty(x_shape, dtype=dtype, device=ref.device) if need_x else None
+        pu = pt = None
+        if g_np is not None:
+            pu = C.c_void_p(g_np.data_ptr())
+            pt = C.c_void_p(g_np.data_ptr() + n * g_np.element_size()) if cfg else None
+        check(_lib.lib().dd_cfg_ddim_bwd(_ptr(g_prev), _ptr(g_x0), n, _DTYPES[dtype], s, a_t, a_prev, int(cfg), pu, pt,
+                                         _ptr(g_x), _stream()), "dd_cfg_ddim_bwd")
+        _count()
+        return g_np, g_x, None, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------
+# K6  channel affine + L-inf projection
+# ------------------------------------------------------------------------------------------------
+def affine_project(x: torch.Tensor, a: torch.Tensor, b: torch.Tensor, radius: float = -1.0,
+                   center: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y = x*(1+a)+b per (batch, channel); clamp to center +- radius when radius >= 0 (center defaults to x).
+    generate_data.py:696, :726-728, :124-137.  a, b: [B,C,1,1] (any float dtype; fp32 inside)."""
+    x = _req(x, "latents")
+    if x.dim() < 2:
+        raise DistDiffError("latents must be [B, C, ...]")
+    BC = x.shape[0] * x.shape[1]
+    HW = x.numel() // max(BC, 1)
+    a32 = _req(a, "channel_noise").reshape(-1).float().contiguous()
+    b32 = _req(b, "channel_noise_bias").reshape(-1).float().contiguous()
+    if a32.numel() != BC or b32.numel() != BC:
+        raise DistDiffError(f"channel params must have B*C = {BC} elements")
+    if center is not None:
+        center = _req(center, "center", x.dtype)
+        if center.shape != x.shape:
+            raise DistDiffError("center must have the shape of the latents")
+    y = torch.empty_like(x)
+    check(_lib.lib().dd_affine_project_fwd(_ptr(x), _ptr(a32), _ptr(b32), _ptr(center), BC, HW, _code(x), float(radius),
+                                           _ptr(y), _stream()), "dd_affine_project_fwd")
+    _count()
+    return y
+
+
+class ChannelAffine(torch.autograd.Function):
+    """Differentiable y = x*(1+a)+b (no clamp) -- the graph root of transform_guidance (generate_data.py:696)."""
+
+    @staticmethod
+    def forward(ctx, x, a, b):
+        y = affine_project(x.detach(), a.detach(), b.detach(), -1.0)
+        ctx.save_for_backward(x, a)
+        ctx.pshape = (a.shape, a.dtype, b.shape, b.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, g_y):
+        x, a = ctx.saved_tensors
+        x = _req(x, "latents")
+        g_y = _req(g_y, "g_y", x.dtype)
+        BC = x.shape[0] * x.shape[1]
+        HW = x.numel() // BC
+        a32 = a.detach().reshape(-1).float().contiguous()
+        g_a = torch.empty(BC, dtype=torch.float32, device=x.device)
+        g_b = torch.empty(BC, dtype=torch.float32, device=x.device)
+        g_x = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        check(_lib.lib().dd_affine_bwd(_ptr(g_y), _ptr(x), _ptr(a32), BC, HW, _code(x), _ptr(g_a), _ptr(g_b), _ptr(g_x),
+                                       _stream()), "dd_affine_bwd")
+        _count()
+        ash, adt, bsh, bdt = ctx.pshape
+        return g_x, g_a.reshape(ash).to(adt), g_b.reshape(bsh).to(bdt)
+
+
+# ------------------------------------------------------------------------------------------------
+# K7  add_noise
+# ------------------------------------------------------------------------------------------------
+def add_noise(x: torch.Tensor, noise: torch.Tensor, a_t: float) -> torch.Tensor:
+    """sqrt(abar_t) x + sqrt(1 - abar_t) noise  (diffusers add_noise at generate_data.py:1176)."""
+    x = _req(x, "original_samples")
+    noise = _req(noise, "noise", x.dtype)
+    if noise.shape != x.shape:
+        raise DistDiffError("noise must have the shape of the samples")
+    out = torch.empty_like(x)
+    check(_lib.lib().dd_add_noise(_ptr(x), _ptr(noise), x.numel(), _code(x), float(a_t), _ptr(out), _stream()),
+          "dd_add_noise")
+    _count()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# K4  prototype energy
+# ------------------------------------------------------------------------------------------------
+_tickets = {}
+
+
+def _ticket(device: torch.device) -> torch.Tensor:
+    key = (device.index, _stream())
+    t = _tickets.get(key)
+    if t is None:
+        t = torch.zeros(1, dtype=torch.int32, device=device)
+        _tickets[key] = t
+    return t
+
+
+def targets_tensor(targets, C_: int, device) -> torch.Tensor:
+    """batch["targets"] (a python list in the reference, generate_data.py:650) -> validated device int64."""
+    if isinstance(targets, torch.Tensor):
+        t = targets.to(device=device, dtype=torch.int64)
+        return t if t.is_contiguous() else t.contiguous()
+    ts = [int(v) for v in targets]
+    if any(v < 0 or v >= C_ for v in ts):
+        raise DistDiffError(f"target class out of range [0, {C_})")
+    return torch.tensor(ts, dtype=torch.int64, device=device)
+
+
+def energy_fwd_bwd(f: torch.Tensor, targets, g: Optional[torch.Tensor], l: Optional[torch.Tensor], gs: float, ls: float,
+                   normalize_f: bool = False):
+    """One launch: (score[0-dim f32], per_sample [B,2], kstar [B] i32, d score/d f [B,D]).
+    generate_data.py:707-717 (normalize_f=False) / :747-759 (True)."""
+    f = _req(f, "image_features", torch.float32)
+    if f.dim() != 2:
+        raise DistDiffError("image_features must be [B, D]")
+    B, D = f.shape
+    if g is None and l is None:
+        raise DistDiffError("at least one of the global / local prototype tables is required")
+    Cn = g.shape[0] if g is not None else l.shape[0]
+    K = 1
+    if g is not None:
+        g = _req(g, "global prototypes", torch.float32)
+        if g.shape != (Cn, D):
+            raise DistDiffError(f"global prototypes must be [C, {D}]")
+    if l is not None:
+        l = _req(l, "local prototypes", torch.float32)
+        if l.dim() != 3 or l.shape[0] != Cn or l.shape[2] != D:
+            raise DistDiffError(f"local prototypes must be [C, K, {D}]")
+        K = l.shape[1]
+    y = targets_tensor(targets, Cn, f.device)
+    if y.numel() != B:
+        raise DistDiffError("one target per sample required")
+    score = torch.empty(1, dtype=torch.float32, device=f.device)
+    per = torch.empty(B, 2, dtype=torch.float32, device=f.device)
+    kstar = torch.empty(B, dtype=torch.int32, device=f.device)
+    grad = torch.empty_like(f)
+    check(_lib.lib().dd_energy_fwd_bwd(_ptr(f), _ptr(y), _ptr(g), _ptr(l), B, D, Cn, K, float(gs), float(ls),
+                                       int(bool(normalize_f)), _ptr(score), _ptr(per), _ptr(kstar), _ptr(grad),
+                                       _ptr(_ticket(f.device)), _stream()), "dd_energy_fwd_bwd")
+    _count()
+    return score.reshape(()), per, kstar, grad
+
+
+class PrototypeEnergy(torch.autograd.Function):
+    """Differentiable score(f): forward launches K4 once and keeps d score/d f; backward is a scale."""
+
+    @staticmethod
+    def forward(ctx, f, targets, g, l, gs, ls, normalize_f):
+        score, _per, _k, grad = energy_fwd_bwd(f.detach(), targets, g, l, gs, ls, normalize_f)
+        ctx.save_for_backward(grad)
+        return score
+
+    @staticmethod
+    def backward(ctx, g_score):
+        (grad,) = ctx.saved_tensors
+        return grad * g_score, None, None, None, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------
+# K1 / K2 / K3 / K3'  prototype construction
+# ------------------------------------------------------------------------------------------------
+def sort_by_class(labels: torch.Tensor, num_classes: int):
+    """Index plumbing (torch): stable sort of the labels -> (perm [N] i64, class_off [C+1] i64)."""
+    labels = _req(labels, "labels").to(torch.int64)
+    if labels.numel() and (int(labels.min()) < 0 or int(labels.max()) >= num_classes):
+        raise DistDiffError(f"label out of range [0, {num_classes})")
+    _, perm = torch.sort(labels, stable=True)
+    counts = torch.bincount(labels, minlength=num_classes)
+    off = torch.zeros(num_classes + 1, dtype=torch.int64, device=labels.device)
+    off[1:] = torch.cumsum(counts, 0)
+    return perm.contiguous(), off
+
+
+def proto_workspace(D: int, C_: int, K: int, device) -> torch.Tensor:
+    nbytes = _lib.lib().dd_proto_workspace_bytes(D, C_, K)
+    return torch.empty(nbytes, dtype=torch.uint8, device=device)
+
+
+def rownorm_classsum(feat: torch.Tensor, perm: Optional[torch.Tensor], class_off: torch.Tensor,
+                     ws: Optional[torch.Tensor] = None):
+    """K1: -> (feat_sorted [N,D] f32 normalised, class_sum [C,D] f64, class_cnt [C] i64).  dataloader.py:677-707."""
+    feat = _req(feat, "features", torch.float32)
+    N, D = feat.shape
+    class_off = _req(class_off, "class_off", torch.int64)
+    C_ = class_off.numel() - 1
+    if perm is not None:
+        perm = _req(perm, "perm", torch.int64)
+    ws = proto_workspace(D, C_, 1, feat.device) if ws is None else ws
+    out = torch.empty_like(feat)
+    csum = torch.empty(C_, D, dtype=torch.float64, device=feat.device)
+    ccnt = torch.empty(C_, dtype=torch.int64, device=feat.device)
+    check(_lib.lib().dd_rownorm_classsum(_ptr(feat), _ptr(perm), _ptr(class_off), N, D, C_, _ptr(out), _ptr(csum),
+                                         _ptr(ccnt), _ptr(ws), ws.numel(), _stream()), "dd_rownorm_classsum")
+    _count(2)
+    return out, csum, ccnt
+
+
+def class_mean(sum_: torch.Tensor, cnt: torch.Tensor, want_unit: bool = True):
+    """K2: fp32 means (+ unit-norm copy) of [.., D] f64 sums / i64 counts.  dataloader.py:707; generate_data.py:1115-1116."""
+    sum_ = _req(sum_, "sum", torch.float64)
+    cnt = _req(cnt, "cnt", torch.int64)
+    D = sum_.shape[-1]
+    R = sum_.numel() // D
+    mean = torch.empty(sum_.shape, dtype=torch.float32, device=sum_.device)
+    unit = torch.empty_like(mean) if want_unit else None
+    check(_lib.lib().dd_class_mean(_ptr(sum_), _ptr(cnt), R, D, _ptr(mean), _ptr(unit), _stream()), "dd_class_mean")
+    _count()
+    return mean, unit
+
+
+def normalize_rows(t: torch.Tensor) -> torch.Tensor:
+    """rows / ||rows||  (generate_data.py:1115-1116, 1121-1122)."""
+    t = _req(t, "prototypes", torch.float32)
+    D = t.shape[-1]
+    out = torch.empty_like(t)
+    check(_lib.lib().dd_normalize_rows(_ptr(t), t.numel() // D, D, _ptr(out), _stream()), "dd_normalize_rows")
+    _count()
+    return out
+
+
+def kmeans_seed(x_sorted: torch.Tensor, row_idx: torch.Tensor):
+    x_sorted = _req(x_sorted, "x_sorted", torch.float32)
+    row_idx = _req(row_idx, "row_idx", torch.int64)
+    D = x_sorted.shape[1]
+    R = row_idx.numel()
+    s = torch.empty(*row_idx.shape, D, dtype=torch.float64, device=x_sorted.device)
+    c = torch.empty(row_idx.shape, dtype=torch.int64, device=x_sorted.device)
+    check(_lib.lib().dd_kmeans_seed(_ptr(x_sorted), _ptr(row_idx), R, D, _ptr(s), _ptr(c), _stream()), "dd_kmeans_seed")
+    _count()
+    return s, c
+
+
+def kmeans_update(sum_: torch.Tensor, cnt: torch.Tensor, centroid: torch.Tensor, cnorm: torch.Tensor) -> None:
+    Cn, K, D = centroid.shape
+    check(_lib.lib().dd_kmeans_update(_ptr(_req(sum_, "sum", torch.float64)), _ptr(_req(cnt, "cnt", torch.int64)), Cn, K, D,
+                                      _ptr(centroid), _ptr(cnorm), _stream()), "dd_kmeans_update")
+    _count()
+
+
+class KMeansBuffers:
+    """Caller-owned buffers of one k-means problem (allocated once, reused every Lloyd iteration)."""
+
+    def __init__(self, N: int, D: int, C_: int, K: int, device):
+        self.centroid = torch.zeros(C_, K, D, dtype=torch.float32, device=device)
+        self.cnorm = torch.zeros(C_, K, dtype=torch.float32, device=device)
+        self.assign = torch.empty(N, dtype=torch.int32, device=device)
+        self.sum = torch.empty(C_, K, D, dtype=torch.float64, device=device)
+        self.cnt = torch.empty(C_, K, dtype=torch.int64, device=device)
+        self.inertia = torch.empty(1, dtype=torch.float64, device=device)
+        self.ws = proto_workspace(D, C_, K, device)
+
+
+def kmeans_assign_accum(x_sorted: torch.Tensor, class_off: torch.Tensor, buf: KMeansBuffers) -> None:
+    """K3: one assignment + accumulation pass; results land in buf.assign / buf.sum / buf.cnt / buf.inertia."""
+    x_sorted = _req(x_sorted, "x_sorted", torch.float32)
+    N, D = x_sorted.shape
+    Cn, K, _ = buf.centroid.shape
+    check(_lib.lib().dd_kmeans_assign_accum(_ptr(x_sorted), _ptr(class_off), N, D, Cn, K, _ptr(buf.centroid), _ptr(buf.cnorm),
+                                            _ptr(buf.assign), _ptr(buf.sum), _ptr(buf.cnt), _ptr(buf.inertia), _ptr(buf.ws),
+                                            buf.ws.numel(), _stream()), "dd_kmeans_assign_accum")
+    _count(2)
+
+
+def agglo_average(x_sorted: torch.Tensor, class_off: torch.Tensor, K: int, max_class_size: int):
+    """K3': -> (labels [N] i32 in class-sorted order, sum [C,K,D] f64, cnt [C,K] i64, status [C] i32)."""
+    x_sorted = _req(x_sorted, "x_sorted", torch.float32)
+    class_off = _req(class_off, "class_off", torch.int64)
+    N, D = x_sorted.shape
+    Cn = class_off.numel() - 1
+    nbytes = _lib.lib().dd_agglo_workspace_bytes(max(int(max_class_size), 1), Cn)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=x_sorted.device)
+    labels = torch.empty(N, dtype=torch.int32, device=x_sorted.device)
+    s = torch.empty(Cn, K, D, dtype=torch.float64, device=x_sorted.device)
+    c = torch.empty(Cn, K, dtype=torch.int64, device=x_sorted.device)
+    status = torch.empty(Cn, dtype=torch.int32, device=x_sorted.device)
+    check(_lib.lib().dd_agglo_average(_ptr(x_sorted), _ptr(class_off), Cn, D, K, max(int(max_class_size), 1), _ptr(labels),
+                                      _ptr(s), _ptr(c), _ptr(status), _ptr(ws), nbytes, _stream()), "dd_agglo_average")
+    _count()
+    return labels, s, c, status
+
+
+# ------------------------------------------------------------------------------------------------
+# NCCL communicator through the C ABI
+# ------------------------------------------------------------------------------------------------
+class Comm:
+    """One NCCL communicator per process; the 128-byte unique id travels through ``exchange`` (a callable
+    rank0_bytes -> bytes on every rank, e.g. a torch.distributed broadcast_object_list)."""
+
+    def __init__(self, rank: int, world: int, exchange):
+        self.rank, self.world = rank, world
+        buf = (C.c_ubyte * 128)()
+        if rank == 0:
+            check(_lib.lib().dd_comm_unique_id(buf), "dd_comm_unique_id")
+        uid = exchange(bytes(buf))
+        buf2 = (C.c_ubyte * 128).from_buffer_copy(uid)
+        handle = C.c_void_p()
+        check(_lib.lib().dd_comm_init(rank, world, buf2, C.byref(handle)), "dd_comm_init")
+        self.handle = handle
+
+    def allreduce(self, sum_: Optional[torch.Tensor], cnt: Optional[torch.Tensor]) -> None:
+        ns = 0 if sum_ is None else sum_.numel()
+        nc = 0 if cnt is None else cnt.numel()
+        if sum_ is not None:
+            _req(sum_, "sum", torch.float64)
+        if cnt is not None:
+            _req(cnt, "cnt", torch.int64)
+        check(_lib.lib().dd_comm_allreduce(self.handle, _ptr(sum_), ns, _ptr(cnt), nc, _stream()), "dd_comm_allreduce")
+
+    def close(self) -> None:
+        if self.handle:
+            check(_lib.lib().dd_comm_destroy(self.handle), "dd_comm_destroy")
+            self.handle = None

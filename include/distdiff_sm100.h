@@ -1,0 +1,156 @@
+/*
+ * distdiff_sm100.h -- C ABI of libdistdiff_sm100.so: the B200 (sm_100a) kernels behind the
+ * hierarchical-prototype energy-guidance hot path of DistDiff (haoweiz23/DistDiff).
+ *
+ * The reference is pure Python/PyTorch and exposes no FFI; its boundary for this path is a set of
+ * Python functions (file:line below, relative to the reference tree).  Every entry point here replaces
+ * the eager-op sequence of one of them; the Python host mirror (distdiff_b200/guidance.py,
+ * distdiff_b200/prototypes.py) keeps the reference's signatures and binds these with ctypes
+ * (INTEGRATION.md shows the stub a reference maintainer would add).
+ *
+ * Conventions
+ *  - plain C: device pointers + sizes; no torch / C++ types.  Buffers are contiguous and owned by the
+ *    caller, including workspaces; the library allocates nothing persistent except NCCL communicators.
+ *  - every call is asynchronous on the given stream (a cudaStream_t passed as void*); no hidden syncs.
+ *  - return 0 on success, otherwise a non-zero code (cudaError_t, or 1000+ncclResult_t, or DD_E*);
+ *    the message is in dd_last_error() (thread-local).  Never throws, never exits.
+ *  - dtype: 0 = f32, 1 = f16, 2 = bf16 (storage type of latents; arithmetic is always fp32).
+ */
+#ifndef DISTDIFF_SM100_H_
+#define DISTDIFF_SM100_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DD_ABI_VERSION 1
+
+#define DD_F32 0
+#define DD_F16 1
+#define DD_BF16 2
+
+#define DD_EINVAL 9001      /* bad argument (null pointer, size, dtype, alignment that cannot be served) */
+#define DD_EUNSUPPORTED 9002 /* shape outside what the sm_100a kernels are built for (e.g. D % 4 != 0)   */
+#define DD_EWORKSPACE 9003  /* workspace too small                                                       */
+
+typedef void* dd_stream_t; /* cudaStream_t */
+
+/* ---- library ---------------------------------------------------------------------------------- */
+int dd_abi_version(void);
+const char* dd_last_error(void);
+/* number of SMs / compute capability of the current device (fails unless it is sm_100). */
+int dd_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- K5: CFG combine + predicted x0 + DDIM step (+ guidance update) ------------------------------
+ * Replaces generate_data.py:115-120 (chunk, sub, mul, add; diffusers DDIMScheduler.step, eta = 0,
+ * epsilon prediction, no clipping) and generate_data.py:762 (x_next - rho * grad):
+ *     eps    = text ? uncond + s * (text - uncond) : uncond
+ *     x0     = (x - sqrt(1 - a_t) * eps) / sqrt(a_t)
+ *     x_prev = sqrt(a_prev) * x0 + sqrt(1 - a_prev) * eps  [- rho * grad]
+ * n = number of elements of x (= B*4*64*64); noise_uncond/noise_text are the two halves of the UNet
+ * output [2B,...] (noise_text may be NULL: no classifier-free guidance); grad may be NULL.
+ * x_prev / x0 may each be NULL (not written). */
+int dd_cfg_ddim_fwd(const void* noise_uncond, const void* noise_text, const void* x, int64_t n, int dtype,
+                    float s, float a_t, float a_prev, const void* grad, float rho, void* x_prev, void* x0,
+                    dd_stream_t stream);
+/* Backward of the above (it sits inside the autograd graph of transform_/direct_guidance,
+ * generate_data.py:700,721 and :741,761).  g_prev / g_x0: upstream grads (either may be NULL = zero).
+ * Outputs (each may be NULL): g_uncond, g_text (to the UNet output halves), g_x (to the latents). */
+int dd_cfg_ddim_bwd(const void* g_prev, const void* g_x0, int64_t n, int dtype, float s, float a_t, float a_prev,
+                    int has_text, void* g_uncond, void* g_text, void* g_x, dd_stream_t stream);
+
+/* ---- K6: channel-affine transform + L-inf projection ---------------------------------------------
+ * Replaces generate_data.py:696 and :726-728 (-> tensor_clamp/linfball_proj :124-137):
+ *     y = x * (1 + a[bc]) + b[bc];  if radius >= 0: y = clamp(y, center - radius, center + radius)
+ * x: [BC, HW] (dtype), a, b: [BC] fp32, center: [BC, HW] (dtype) or NULL (= x).  radius < 0: no clamp. */
+int dd_affine_project_fwd(const void* x, const float* a, const float* b, const void* center, int64_t BC,
+                          int64_t HW, int dtype, float radius, void* y, dd_stream_t stream);
+/* Backward of y = x*(1+a)+b (no clamp), generate_data.py:721:  g_a[bc] = sum_hw g*x, g_b[bc] = sum_hw g,
+ * optional g_x = g * (1 + a).  Deterministic (fixed-order tree per row). */
+int dd_affine_bwd(const void* g_y, const void* x, const float* a, int64_t BC, int64_t HW, int dtype, float* g_a,
+                  float* g_b, void* g_x, dd_stream_t stream);
+
+/* ---- K7: forward-diffusion noising --------------------------------------------------------------
+ * Replaces diffusers DDIMScheduler.add_noise at generate_data.py:1176:
+ *     out = sqrt(a_t) * x + sqrt(1 - a_t) * noise */
+int dd_add_noise(const void* x, const void* noise, int64_t n, int dtype, float a_t, void* out, dd_stream_t stream);
+
+/* ---- K4: hierarchical prototype energy, forward + analytic gradient -------------------------------
+ * Replaces generate_data.py:707-717 / :747-759 and their autograd backward:
+ *     fn    = normalize_f ? f / ||f|| : f                                   (direct mode, :747)
+ *     score = gs * mean_b ||fn_b - g[y_b]|| + ls * mean_b ||fn_b - l[y_b, k*_b]||
+ *     k*_b  = argmax_k <fn_b, l[y_b, k]>   (first max on ties)
+ *     grad_f = d score / d f   (0 where a distance is exactly 0, like torch.norm)
+ * f: [B,D] f32; target: [B] i64 in [0,C); g: [C,D] f32 or NULL; l: [C,K,D] f32 or NULL (prototypes are
+ * used as given -- the caller normalises them once, generate_data.py:1113-1127).
+ * Outputs: score [1] f32 (deterministic fixed-order sum), per_sample [B,2] f32 (the two distances),
+ * kstar [B] i32, grad_f [B,D] f32.  ticket: [1] u32 device word, zero before first use (self-resetting). */
+int dd_energy_fwd_bwd(const float* f, const int64_t* target, const float* g, const float* l, int B, int D, int C,
+                      int K, float gs, float ls, int normalize_f, float* score, float* per_sample, int32_t* kstar,
+                      float* grad_f, unsigned int* ticket, dd_stream_t stream);
+
+/* ---- K1/K2: feature normalisation, class gather, class means --------------------------------------
+ * Replaces dataloader.py:677 (f / ||f||), :678-697 (D2H + python per-class gather) and :707 (class mean).
+ * feat: [N,D] f32 raw guide features in dataset order; perm: [N] i64, the stable sort of the labels
+ * (row perm[i] of feat is the i-th row in class-sorted order); class_off: [C+1] i64 offsets into the
+ * sorted order.  Writes feat_sorted [N,D] f32 (L2-normalised rows, class-sorted, dataset order inside a
+ * class) and class_sum [C,D] f64 / class_cnt [C] i64 (this rank's contribution -- all-reduce them when the
+ * samples are sharded over GPUs).  ws: dd_proto_workspace_bytes(D, C, 1, grid) bytes. */
+size_t dd_proto_workspace_bytes(int D, int C, int K);
+int dd_rownorm_classsum(const float* feat, const int64_t* perm, const int64_t* class_off, int64_t N, int D, int C,
+                        float* feat_sorted, double* class_sum, int64_t* class_cnt, void* ws, size_t ws_bytes,
+                        dd_stream_t stream);
+/* mean[c] = fp32(class_sum[c] / class_cnt[c]) (what the reference stores, dataloader.py:707,729) and
+ * mean_unit[c] = mean[c] / ||mean[c]|| (generate_data.py:1115-1116); either output may be NULL.
+ * Works for any [R,D] (R = C for class means, R = C*K for group prototypes). Rows with cnt == 0 -> 0. */
+int dd_class_mean(const double* sum, const int64_t* cnt, int64_t R, int D, float* mean, float* mean_unit,
+                  dd_stream_t stream);
+/* rows / ||rows|| for a ready [R,D] f32 prototype table (generate_data.py:1115-1116, 1121-1122). */
+int dd_normalize_rows(const float* in, int64_t R, int D, float* out, dd_stream_t stream);
+
+/* ---- K3: per-class k-means (north-star extension; the reference clusters with K3') ----------------
+ * x_sorted / class_off as produced by dd_rownorm_classsum.  One Lloyd iteration =
+ * dd_kmeans_assign_accum -> [all-reduce sum/cnt over ranks] -> dd_kmeans_update.
+ * Seeding (spec: centroid[c,k] = the floor(k*n_c/K)-th row of class c in dataset order) is a row gather:
+ * dd_kmeans_seed writes sum[r] = x_sorted[row_idx[r]] (as f64), cnt[r] = 1 for row_idx[r] >= 0 and zeros
+ * otherwise (row owned by another rank); all-reduce, then dd_kmeans_update turns it into centroids. */
+int dd_kmeans_seed(const float* x_sorted, const int64_t* row_idx, int64_t R, int D, double* sum, int64_t* cnt,
+                   dd_stream_t stream);
+/* assign[i] = argmin_k (cnorm[c,k] - 2 <x_i, centroid[c,k]>) (lowest k on ties), sum[c,k] += x_i (fp64),
+ * cnt[c,k] += 1, inertia += ||x_i - centroid[c,k*]||^2.  sum/cnt/inertia are overwritten (not accumulated). */
+int dd_kmeans_assign_accum(const float* x_sorted, const int64_t* class_off, int64_t N, int D, int C, int K,
+                           const float* centroid, const float* cnorm, int32_t* assign, double* sum, int64_t* cnt,
+                           double* inertia, void* ws, size_t ws_bytes, dd_stream_t stream);
+/* centroid[c,k] = fp32(sum/cnt) where cnt > 0 (an empty cluster keeps its centroid); cnorm = ||centroid||^2. */
+int dd_kmeans_update(const double* sum, const int64_t* cnt, int C, int K, int D, float* centroid, float* cnorm,
+                     dd_stream_t stream);
+
+/* ---- K3': per-class average-linkage agglomerative clustering (reference-exact) --------------------
+ * Replaces dataloader.py:699-705,710-722: sklearn AgglomerativeClustering(K, linkage='average') ->
+ * scipy linkage(X,'average','euclidean') (fp64 pdist) -> _hc_cut labels -> per-cluster means.
+ * One CTA per class: fp64 distance matrix in ws, globally-closest-pair merges with the Lance-Williams
+ * average update, children (min id, max id), _hc_cut heap walk, labels in sklearn's numbering.
+ * labels: [N] i32 (class-sorted order); sum [C,K,D] f64, cnt [C,K] i64 (feed dd_class_mean);
+ * status [C] i32: 0 ok, 1 = class has < 2 samples, 2 = class has < K samples (sklearn raises for both).
+ * ws: dd_agglo_workspace_bytes(max_n, C). */
+size_t dd_agglo_workspace_bytes(int64_t max_class_size, int C);
+int dd_agglo_average(const float* x_sorted, const int64_t* class_off, int C, int D, int K, int64_t max_class_size,
+                     int32_t* labels, double* sum, int64_t* cnt, int32_t* status, void* ws, size_t ws_bytes,
+                     dd_stream_t stream);
+
+/* ---- NCCL plumbing for the sharded prototype stage ---------------------------------------------
+ * samples sharded per GPU; class sums/counts (K1) and centroid sums/counts (K3, every Lloyd iteration)
+ * are all-reduced over NVLink.  unique_id: 128 bytes (ncclUniqueId), created on rank 0 and broadcast by
+ * the host (torch.distributed store). */
+int dd_comm_unique_id(void* unique_id_128);
+int dd_comm_init(int rank, int world, const void* unique_id_128, void** comm);
+int dd_comm_allreduce(void* comm, double* sum, size_t n_sum, int64_t* cnt, size_t n_cnt, dd_stream_t stream);
+int dd_comm_destroy(void* comm);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DISTDIFF_SM100_H_ */

@@ -1,0 +1,407 @@
+"""GPU parity tests: every kernel of libdistdiff_sm100.so, called through the C ABI (ctypes, via
+distdiff_b200.ops), against the CPU oracle on the same seeded inputs and against the committed golden
+vectors produced by the reference's own function bodies.
+
+Tolerances (north_star): fp32 elementwise kernels are BIT-EXACT against the oracle's fp32 op sequence;
+reductions (energy, prototypes) within 1e-5 relative (prototypes) / 1e-5 (energy score & gradient, fp32
+accumulation order differs); indices (k*, assignments, agglomerative labels) exact; fp16/bf16 storage:
+one rounding of the fp32 result (<= 1 ulp of the storage type, stated per test).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ddim, energy, guidance, prototypes
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops(cuda_device):
+    from distdiff_b200 import ops as _ops
+    return _ops
+
+
+def _g(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+# ------------------------------------------------------------------------------------------- K5
+@pytest.mark.parametrize("shape", [(1, 4, 64, 64), (2, 4, 64, 64), (3, 4, 8, 8), (2, 3, 5, 7)])
+@pytest.mark.parametrize("cfg", [True, False])
+@pytest.mark.parametrize("with_grad", [False, True])
+def test_cfg_ddim_fwd_fp32_bitexact(ops, cuda_device, shape, cfg, with_grad):
+    g = _g(1)
+    x = torch.randn(shape, generator=g)
+    npred = torch.randn((2 * shape[0] if cfg else shape[0],) + shape[1:], generator=g)
+    grad = torch.randn(shape, generator=g) if with_grad else None
+    for t in (981, 381, 1):
+        a_t, a_prev = ddim.alpha_pair(t)
+        if cfg:
+            rp, r0 = ddim.cfg_ddim_step(npred, x, 7.5, a_t, a_prev, grad, 10.0)
+        else:
+            rp, r0 = ddim.ddim_step(npred, x, a_t, a_prev)
+            if grad is not None:
+                rp = rp - 10.0 * grad
+        p, x0 = ops.cfg_ddim_step(npred.to(cuda_device), x.to(cuda_device), 7.5, float(a_t), float(a_prev), cfg=cfg,
+                                  grad=None if grad is None else grad.to(cuda_device), rho=10.0)
+        assert torch.equal(p.cpu(), rp), (t, (p.cpu() - rp).abs().max())
+        assert torch.equal(x0.cpu(), r0)
+
+
+def test_cfg_ddim_fwd_golden(ops, cuda_device, golden):
+    for name in ("guidance_small", "guidance_d2048", "guidance_b1"):
+        c = golden[name]
+        a_t, a_prev = ddim.alpha_pair(c["denoise"]["t"])
+        p, x0 = ops.cfg_ddim_step(c["denoise"]["noise_pred"].to(cuda_device), c["latents"].to(cuda_device),
+                                  c["args"]["guidance_scale"], float(a_t), float(a_prev))
+        assert torch.equal(p.cpu(), c["denoise"]["prev"]) and torch.equal(x0.cpu(), c["denoise"]["x0"])
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float16, 2 ** -10), (torch.bfloat16, 2 ** -7)])
+def test_cfg_ddim_fwd_half(ops, cuda_device, dtype, tol):
+    """16-bit storage: fp32 arithmetic, one rounding -> within 1 ulp (relative 2^-10 fp16 / 2^-7 bf16) of the
+    fp32 oracle evaluated on the same (already rounded) inputs."""
+    g = _g(2)
+    x = torch.randn(4, 4, 64, 64, generator=g).to(dtype)
+    npred = torch.randn(8, 4, 64, 64, generator=g).to(dtype)
+    a_t, a_prev = ddim.alpha_pair(481)
+    rp, r0 = ddim.cfg_ddim_step(npred.float(), x.float(), 7.5, a_t, a_prev)
+    p, x0 = ops.cfg_ddim_step(npred.to(cuda_device), x.to(cuda_device), 7.5, float(a_t), float(a_prev))
+    assert p.dtype == dtype
+    assert torch.allclose(p.float().cpu(), rp, rtol=tol, atol=tol * 1e-2)
+    assert torch.allclose(x0.float().cpu(), r0, rtol=tol, atol=tol * 1e-2)
+    assert torch.equal(p.cpu(), rp.to(dtype)) and torch.equal(x0.cpu(), r0.to(dtype))  # exactly one rounding
+
+
+@pytest.mark.parametrize("cfg", [True, False])
+def test_cfg_ddim_bwd_vs_autograd(ops, cuda_device, cfg):
+    g = _g(3)
+    B = 2
+    x = torch.randn(B, 4, 16, 16, generator=g, dtype=torch.float64, requires_grad=True)
+    npred = torch.randn(2 * B if cfg else B, 4, 16, 16, generator=g, dtype=torch.float64, requires_grad=True)
+    wp = torch.randn(B, 4, 16, 16, generator=g, dtype=torch.float64)
+    w0 = torch.randn(B, 4, 16, 16, generator=g, dtype=torch.float64)
+    a_t, a_prev = (v.double() for v in ddim.alpha_pair(381))
+    if cfg:
+        rp, r0 = ddim.cfg_ddim_step(npred, x, 7.5, a_t, a_prev)
+    else:
+        rp, r0 = ddim.ddim_step(npred, x, a_t, a_prev)
+    ((rp * wp).sum() + (r0 * w0).sum()).backward()
+
+    xc = x.detach().float().to(cuda_device).requires_grad_(True)
+    nc = npred.detach().float().to(cuda_device).requires_grad_(True)
+    p, x0 = ops.CfgDdimStep.apply(nc, xc, 7.5, float(a_t), float(a_prev), cfg)
+    ((p * wp.float().to(cuda_device)).sum() + (x0 * w0.float().to(cuda_device)).sum()).backward()
+    assert torch.allclose(xc.grad.cpu().double(), x.grad, rtol=1e-5, atol=1e-5)
+    assert torch.allclose(nc.grad.cpu().double(), npred.grad, rtol=1e-5, atol=1e-4)
+    # only x0 used (direct_guidance): g_prev is None
+    xc.grad = None; nc.grad = None
+    p, x0 = ops.CfgDdimStep.apply(nc, xc, 7.5, float(a_t), float(a_prev), cfg)
+    (x0 * w0.float().to(cuda_device)).sum().backward()
+    x.grad = None; npred.grad = None
+    if cfg:
+        _, r0 = ddim.cfg_ddim_step(npred, x, 7.5, a_t, a_prev)
+    else:
+        _, r0 = ddim.ddim_step(npred, x, a_t, a_prev)
+    (r0 * w0).sum().backward()
+    assert torch.allclose(xc.grad.cpu().double(), x.grad, rtol=1e-5, atol=1e-5)
+    assert torch.allclose(nc.grad.cpu().double(), npred.grad, rtol=1e-5, atol=1e-4)
+
+
+# ------------------------------------------------------------------------------------------- K6 / K7
+@pytest.mark.parametrize("shape", [(2, 4, 64, 64), (1, 4, 8, 8), (3, 5, 3, 3)])
+@pytest.mark.parametrize("radius", [-1.0, 0.2, 0.8])
+def test_affine_project_fp32_bitexact(ops, cuda_device, shape, radius):
+    g = _g(4)
+    x = torch.randn(shape, generator=g)
+    a = torch.rand(shape[0], shape[1], 1, 1, generator=g)
+    b = torch.randn(shape[0], shape[1], 1, 1, generator=g)
+    ref = guidance.affine_project(x, a, b, radius if radius >= 0 else None)
+    if radius >= 0:  # literally the reference sequence: transform then in-place masked clamp
+        lit = x * (1 + a) + b
+        guidance.linfball_proj(x.clone(), radius, lit, in_place=True)
+        assert torch.equal(lit, ref)
+    y = ops.affine_project(x.to(cuda_device), a.to(cuda_device), b.to(cuda_device), radius)
+    assert torch.equal(y.cpu(), ref)
+
+
+def test_linfball_golden(ops, cuda_device, golden):
+    c = golden["linfball"]
+    B, Cc = c["t"].shape[:2]
+    z = torch.zeros(B, Cc, 1, 1)
+    y = ops.affine_project(c["t"].to(cuda_device), z.to(cuda_device), z.to(cuda_device), c["radius"],
+                           center=c["center"].to(cuda_device))
+    assert torch.equal(y.cpu(), c["out"])
+
+
+def test_affine_bwd_vs_autograd(ops, cuda_device):
+    g = _g(5)
+    x = torch.randn(3, 4, 64, 64, generator=g, dtype=torch.float64)
+    a = torch.rand(3, 4, 1, 1, generator=g, dtype=torch.float64, requires_grad=True)
+    b = torch.randn(3, 4, 1, 1, generator=g, dtype=torch.float64, requires_grad=True)
+    w = torch.randn(3, 4, 64, 64, generator=g, dtype=torch.float64)
+    ((x * (1 + a) + b) * w).sum().backward()
+    xc = x.float().to(cuda_device).requires_grad_(True)
+    ac = a.detach().float().to(cuda_device).requires_grad_(True)
+    bc = b.detach().float().to(cuda_device).requires_grad_(True)
+    (ops.ChannelAffine.apply(xc, ac, bc) * w.float().to(cuda_device)).sum().backward()
+    assert torch.allclose(ac.grad.cpu().double(), a.grad, rtol=1e-5, atol=1e-3)
+    assert torch.allclose(bc.grad.cpu().double(), b.grad, rtol=1e-5, atol=1e-3)
+    assert torch.allclose(xc.grad.cpu().double(), w * (1 + a.detach()), rtol=1e-6, atol=1e-6)
+    # determinism: two runs are bit-identical
+    ac2 = a.detach().float().to(cuda_device).requires_grad_(True)
+    bc2 = b.detach().float().to(cuda_device).requires_grad_(True)
+    (ops.ChannelAffine.apply(xc.detach(), ac2, bc2) * w.float().to(cuda_device)).sum().backward()
+    assert torch.equal(ac2.grad, ac.grad) and torch.equal(bc2.grad, bc.grad)
+
+
+@pytest.mark.parametrize("shape", [(2, 4, 64, 64), (1, 3, 5, 7)])
+def test_add_noise_bitexact(ops, cuda_device, shape):
+    g = _g(6)
+    x = torch.randn(shape, generator=g); n = torch.randn(shape, generator=g)
+    for t in (981, 481, 1):
+        a_t = ddim.alphas_cumprod()[t]
+        out = ops.add_noise(x.to(cuda_device), n.to(cuda_device), float(a_t))
+        assert torch.equal(out.cpu(), ddim.add_noise(x, n, a_t))
+
+
+# ------------------------------------------------------------------------------------------- K4
+def _energy_case(B, C, K, D, seed, dup=False):
+    g = _g(seed)
+    f = torch.randn(B, D, generator=g)
+    gp = torch.nn.functional.normalize(torch.randn(C, D, generator=g), dim=-1)
+    lp = torch.nn.functional.normalize(torch.randn(C, K, D, generator=g), dim=-1)
+    if dup and K > 1:
+        lp[:, 1] = lp[:, 0]  # exact argmax ties -> first max must win
+    y = torch.randint(0, C, (B,), generator=g).tolist()
+    return f, gp, lp, y
+
+
+@pytest.mark.parametrize("B,C,K,D", [(1, 5, 3, 64), (2, 100, 3, 2048), (16, 100, 3, 2048), (7, 10, 10, 1280),
+                                     (5, 4, 1, 512), (1024, 100, 3, 2048), (2000, 50, 10, 2048), (1500, 7, 5, 512)])
+@pytest.mark.parametrize("normalize_f", [False, True])
+def test_energy_vs_oracle(ops, cuda_device, B, C, K, D, normalize_f):
+    f, gp, lp, y = _energy_case(B, C, K, D, 10 + B)
+    for G, L in ((gp, lp), (gp, None), (None, lp)):
+        s_ref, per_ref, k_ref, g_ref = energy.energy_fwd_bwd(f.numpy(), y, None if G is None else G.numpy(),
+                                                             None if L is None else L.numpy(), 0.7, 1.3, normalize_f)
+        score, per, kstar, grad = ops.energy_fwd_bwd(f.to(cuda_device), y, None if G is None else G.to(cuda_device),
+                                                     None if L is None else L.to(cuda_device), 0.7, 1.3, normalize_f)
+        assert abs(float(score) - float(s_ref)) <= 1e-5 * abs(float(s_ref))
+        assert np.allclose(per.cpu().numpy(), per_ref, rtol=1e-5, atol=1e-6)
+        if L is not None:
+            # k* exact, except where the oracle's own top-2 dots are closer than fp32 resolution (documented tie)
+            fn = f.double() / f.double().norm(dim=-1, keepdim=True) if normalize_f else f.double()
+            dots = torch.einsum("bd,bkd->bk", fn, L.double()[y])
+            top2 = dots.topk(min(2, K), dim=-1).values
+            clear = (top2[:, 0] - top2[:, -1]).abs() > 1e-5 * dots.abs().max() if K > 1 else torch.ones(B, dtype=torch.bool)
+            assert np.array_equal(kstar.cpu().numpy()[clear.numpy()], k_ref[clear.numpy()])
+            assert clear.float().mean() > 0.99
+        gn = np.linalg.norm(g_ref)
+        assert np.linalg.norm(grad.cpu().numpy() - g_ref) <= 1e-5 * gn
+
+
+def test_energy_vs_autograd_of_literal_restatement(ops, cuda_device):
+    f, gp, lp, y = _energy_case(6, 9, 3, 2048, 77)
+    for normalize_f in (False, True):
+        fr = f.clone().requires_grad_(True)
+        s = energy.energy_score(fr, y, gp, lp, 1.0, 1.0, normalize_f=normalize_f)
+        (gr,) = torch.autograd.grad(s, fr)
+        fc = f.to(cuda_device).requires_grad_(True)
+        sc = ops.PrototypeEnergy.apply(fc, y, gp.to(cuda_device), lp.to(cuda_device), 1.0, 1.0, normalize_f)
+        (2.0 * sc).backward()
+        assert abs(float(sc) - float(s)) < 1e-5 * abs(float(s))
+        assert torch.allclose(fc.grad.cpu(), 2.0 * gr, rtol=1e-4, atol=1e-7)
+
+
+def test_energy_ties_and_zero_distance(ops, cuda_device):
+    f, gp, lp, y = _energy_case(8, 6, 4, 256, 5, dup=True)
+    _, _, kstar, _ = ops.energy_fwd_bwd(f.to(cuda_device), y, gp.to(cuda_device), lp.to(cuda_device), 1.0, 1.0, False)
+    _, _, k_ref, _ = energy.energy_fwd_bwd(f.numpy(), y, gp.numpy(), lp.numpy(), 1.0, 1.0, False)
+    assert np.array_equal(kstar.cpu().numpy(), k_ref)
+    assert not np.any(kstar.cpu().numpy() == 1)  # duplicate of index 0 never wins
+    # f exactly on its class prototype: distance 0 -> gradient 0 (torch.norm sub-gradient), no NaN
+    y2 = [1, 2, 3]
+    f2 = gp[y2].clone()
+    score, per, _, grad = ops.energy_fwd_bwd(f2.to(cuda_device), y2, gp.to(cuda_device), None, 1.0, 1.0, False)
+    assert float(score) == 0.0 and torch.count_nonzero(grad) == 0 and torch.isfinite(grad).all()
+
+
+def test_energy_deterministic_and_bad_target(ops, cuda_device):
+    f, gp, lp, y = _energy_case(3000, 20, 3, 2048, 9)
+    a = ops.energy_fwd_bwd(f.to(cuda_device), y, gp.to(cuda_device), lp.to(cuda_device), 1.0, 1.0, True)
+    b = ops.energy_fwd_bwd(f.to(cuda_device), y, gp.to(cuda_device), lp.to(cuda_device), 1.0, 1.0, True)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[3], b[3])
+    from distdiff_b200._lib import DistDiffError
+    with pytest.raises(DistDiffError):
+        ops.energy_fwd_bwd(f[:2].to(cuda_device), [0, 20], gp.to(cuda_device), None, 1.0, 1.0)
+    with pytest.raises(DistDiffError):
+        ops.energy_fwd_bwd(f[:2], [0, 1], gp, None, 1.0, 1.0)  # CPU tensors: no fallback
+
+
+# ------------------------------------------------------------------------------------------- K1 / K2
+def _features(N, C, D, seed, ragged=True):
+    rng = np.random.default_rng(seed)
+    if ragged:
+        labels = rng.integers(0, C, size=N)
+        labels[:C] = np.arange(C) if N >= C else labels[:C]
+    else:
+        labels = np.arange(N) % C
+    centers = rng.normal(size=(C, 4, D)).astype(np.float32)
+    feats = centers[labels, rng.integers(0, 4, size=N)] * 1.5 + rng.normal(size=(N, D)).astype(np.float32)
+    return feats.astype(np.float32), labels.astype(np.int64)
+
+
+@pytest.mark.parametrize("N,C,D", [(300, 10, 64), (3000, 100, 2048), (50, 7, 1280), (5000, 3, 512), (40, 60, 2048)])
+def test_rownorm_classsum_vs_oracle(ops, cuda_device, N, C, D):
+    feats, labels = _features(N, C, D, N + C, ragged=True)
+    if N < C:
+        labels = np.random.default_rng(0).integers(0, C, size=N)  # some classes empty
+    ft = torch.from_numpy(feats).to(cuda_device)
+    perm, off = ops.sort_by_class(torch.from_numpy(labels).to(cuda_device), C)
+    xs, csum, ccnt = ops.rownorm_classsum(ft, perm, off)
+    ref = prototypes.l2_normalize_rows(feats)
+    order = np.argsort(labels, kind="stable")
+    assert np.array_equal(perm.cpu().numpy(), order)
+    assert np.allclose(xs.cpu().numpy(), ref[order], rtol=2e-7, atol=1e-9)
+    assert np.array_equal(ccnt.cpu().numpy(), np.bincount(labels, minlength=C))
+    ref_sum = np.zeros((C, D)); np.add.at(ref_sum, labels, ref.astype(np.float64))
+    assert np.allclose(csum.cpu().numpy(), ref_sum, rtol=1e-6, atol=1e-7)
+    mean, unit = ops.class_mean(csum, ccnt)
+    nz = np.bincount(labels, minlength=C) > 0
+    ref_mean = np.stack([ref[labels == c].mean(0) if nz[c] else np.zeros(D, np.float32) for c in range(C)])
+    assert np.allclose(mean.cpu().numpy(), ref_mean, rtol=1e-5, atol=1e-8)
+    g_unit, _ = prototypes.normalize_prototypes(ref_mean[nz], ref_mean[nz][:, None, :])
+    assert np.allclose(unit.cpu().numpy()[nz], g_unit, rtol=1e-5, atol=1e-8)
+    # bit-reproducible
+    xs2, csum2, _ = ops.rownorm_classsum(ft, perm, off)
+    assert torch.equal(xs, xs2) and torch.equal(csum, csum2)
+
+
+@pytest.mark.parametrize("name", ["proto_caltech_like", "proto_d2048", "proto_k5"])
+def test_class_means_golden(ops, cuda_device, golden, name):
+    c = golden[name]
+    C = int(c["labels"].max()) + 1
+    perm, off = ops.sort_by_class(c["labels"].to(cuda_device), C)
+    xs, csum, ccnt = ops.rownorm_classsum(c["features"].to(cuda_device), perm, off)
+    mean, _ = ops.class_mean(csum, ccnt, want_unit=False)
+    ref = c["global_prototypes"].numpy()
+    assert np.linalg.norm(mean.cpu().numpy() - ref, axis=-1).max() <= 1e-5 * np.linalg.norm(ref, axis=-1).min()
+    assert np.allclose(mean.cpu().numpy(), ref, rtol=1e-5, atol=1e-8)
+
+
+# ------------------------------------------------------------------------------------------- K3'
+@pytest.mark.parametrize("name", ["proto_caltech_like", "proto_d2048", "proto_k5"])
+def test_agglomerative_golden(ops, cuda_device, golden, name):
+    c = golden[name]
+    K = c["K"]
+    labels_np = c["labels"].numpy()
+    C = int(labels_np.max()) + 1
+    perm, off = ops.sort_by_class(c["labels"].to(cuda_device), C)
+    xs, _, ccnt = ops.rownorm_classsum(c["features"].to(cuda_device), perm, off)
+    lab, s, n, status = ops.agglo_average(xs, off, K, int(ccnt.max()))
+    assert int(status.abs().sum()) == 0
+    local, _ = ops.class_mean(s, n, want_unit=False)
+    ref = c["local_prototypes"].numpy()
+    assert np.allclose(local.cpu().numpy(), ref, rtol=1e-5, atol=1e-8)     # sklearn's cluster numbering too
+    # labels == sklearn's, class by class
+    fn = prototypes.l2_normalize_rows(c["features"].numpy())
+    _, _, ref_labels = prototypes.extract_prototype_from_features(fn, labels_np.tolist(), K)
+    offc = off.cpu().numpy(); labc = lab.cpu().numpy()
+    for ci in range(C):
+        assert np.array_equal(labc[offc[ci]:offc[ci + 1]], ref_labels[ci])
+
+
+@pytest.mark.parametrize("N,C,D,K", [(600, 12, 64, 3), (900, 6, 256, 4), (400, 5, 2048, 3), (1200, 4, 32, 10), (300, 20, 128, 1)])
+def test_agglomerative_vs_sklearn_random(ops, cuda_device, N, C, D, K):
+    feats, labels = _features(N, C, D, 3 * N + K, ragged=True)
+    fn = prototypes.l2_normalize_rows(feats)
+    gl, lc, ref_labels = prototypes.extract_prototype_from_features(fn, labels.tolist(), K)
+    perm, off = ops.sort_by_class(torch.from_numpy(labels).to(cuda_device), C)
+    xs, _, ccnt = ops.rownorm_classsum(torch.from_numpy(feats).to(cuda_device), perm, off)
+    lab, s, n, status = ops.agglo_average(xs, off, K, int(ccnt.max()))
+    assert int(status.abs().sum()) == 0
+    offc = off.cpu().numpy(); labc = lab.cpu().numpy()
+    for ci in range(C):
+        assert np.array_equal(labc[offc[ci]:offc[ci + 1]], ref_labels[ci]), ci
+    local, _ = ops.class_mean(s, n, want_unit=False)
+    assert np.allclose(local.cpu().numpy(), lc, rtol=1e-5, atol=1e-7)
+
+
+def test_agglomerative_error_status(ops, cuda_device):
+    # class 0: 1 sample (sklearn: "at least 2 samples"), class 1: 2 samples < K=3, class 2: fine
+    feats = np.random.default_rng(1).normal(size=(8, 64)).astype(np.float32)
+    labels = np.array([0, 1, 1, 2, 2, 2, 2, 2])
+    perm, off = ops.sort_by_class(torch.from_numpy(labels).to(cuda_device), 3)
+    xs, _, _ = ops.rownorm_classsum(torch.from_numpy(feats).to(cuda_device), perm, off)
+    _, _, _, status = ops.agglo_average(xs, off, 3, 5)
+    assert status.cpu().tolist() == [1, 2, 0]
+
+
+# ------------------------------------------------------------------------------------------- K3
+def _kmeans_problem(ops, dev, N, C, D, K, seed):
+    feats, labels = _features(N, C, D, seed, ragged=True)
+    perm, off = ops.sort_by_class(torch.from_numpy(labels).to(dev), C)
+    xs, _, ccnt = ops.rownorm_classsum(torch.from_numpy(feats).to(dev), perm, off)
+    return feats, labels, xs, off, ccnt
+
+
+@pytest.mark.parametrize("N,C,D,K", [(4000, 10, 2048, 3), (3000, 100, 2048, 3), (6000, 7, 512, 10), (2500, 5, 1280, 5),
+                                     (5000, 4, 2048, 8), (700, 3, 64, 1), (3000, 6, 2048, 7), (2000, 3, 256, 12)])
+def test_kmeans_one_iteration_vs_oracle(ops, cuda_device, N, C, D, K):
+    feats, labels, xs, off, ccnt = _kmeans_problem(ops, cuda_device, N, C, D, K, N + K)
+    xs_np = xs.cpu().numpy(); offc = off.cpu().numpy()
+    buf = ops.KMeansBuffers(N, D, C, K, cuda_device)
+    rng = np.random.default_rng(K)
+    mu = np.stack([xs_np[offc[c]:offc[c + 1]][rng.choice(offc[c + 1] - offc[c], K, replace=False)] for c in range(C)])
+    mu = (mu + 0.05 * rng.normal(size=mu.shape)).astype(np.float32)
+    buf.centroid.copy_(torch.from_numpy(mu))
+    buf.cnorm.copy_(torch.from_numpy((mu.astype(np.float64) ** 2).sum(-1).astype(np.float32)))
+    ops.kmeans_assign_accum(xs, off, buf)
+    assign = buf.assign.cpu().numpy()
+    inert_ref = 0.0
+    for c in range(C):
+        Xc = xs_np[offc[c]:offc[c + 1]]
+        a_ref, s = prototypes.kmeans_assign(Xc, mu[c])
+        srt = np.sort(s, axis=-1)
+        clear = (srt[:, 1] - srt[:, 0] > 1e-5) if K > 1 else np.ones(len(Xc), bool)   # documented tie: top-2 gap <= 1e-5
+        a = assign[offc[c]:offc[c + 1]]
+        assert np.array_equal(a[clear], a_ref[clear]), c
+        assert clear.mean() > 0.995
+        sums_ref, cnt_ref = prototypes.kmeans_sums(Xc, a, K)        # sums for the GPU's own assignment
+        assert np.array_equal(buf.cnt[c].cpu().numpy(), cnt_ref)
+        scale = np.abs(sums_ref).max() + 1e-30
+        assert np.abs(buf.sum[c].cpu().numpy() - sums_ref).max() <= 2e-6 * scale
+        inert_ref += (((Xc.astype(np.float64) - mu[c][a].astype(np.float64)) ** 2).sum())
+    assert abs(float(buf.inertia) - inert_ref) <= 1e-4 * inert_ref + 1e-6
+    # reproducible bit for bit
+    s1 = buf.sum.clone(); a1 = buf.assign.clone()
+    ops.kmeans_assign_accum(xs, off, buf)
+    assert torch.equal(s1, buf.sum) and torch.equal(a1, buf.assign)
+    # update kernel
+    old = buf.centroid.clone()
+    ops.kmeans_update(buf.sum, buf.cnt, buf.centroid, buf.cnorm)
+    cnt = buf.cnt.cpu().numpy()
+    new_ref = np.where(cnt[..., None] > 0, (buf.sum.cpu().numpy() / np.maximum(cnt, 1)[..., None]).astype(np.float32),
+                       old.cpu().numpy())
+    assert np.array_equal(buf.centroid.cpu().numpy(), new_ref)
+    assert np.allclose(buf.cnorm.cpu().numpy(), (new_ref.astype(np.float64) ** 2).sum(-1), rtol=1e-6)
+
+
+def test_kmeans_tiny_and_empty(ops, cuda_device):
+    # fewer rows than CTAs, an empty class in the middle, N == 0
+    feats = np.random.default_rng(2).normal(size=(9, 64)).astype(np.float32)
+    labels = np.array([0, 0, 0, 2, 2, 2, 2, 3, 3])
+    perm, off = ops.sort_by_class(torch.from_numpy(labels).to(cuda_device), 4)
+    xs, csum, ccnt = ops.rownorm_classsum(torch.from_numpy(feats).to(cuda_device), perm, off)
+    assert ccnt.cpu().tolist() == [3, 0, 4, 2] and float(csum[1].abs().sum()) == 0.0
+    buf = ops.KMeansBuffers(9, 64, 4, 2, cuda_device)
+    buf.centroid.copy_(torch.randn(4, 2, 64)); buf.cnorm.copy_((buf.centroid.double() ** 2).sum(-1).float())
+    ops.kmeans_assign_accum(xs, off, buf)
+    assert buf.cnt.sum(-1).cpu().tolist() == [3, 0, 4, 2]
+    xs0 = torch.empty(0, 64, device=cuda_device)
+    off0 = torch.zeros(5, dtype=torch.int64, device=cuda_device)
+    buf0 = ops.KMeansBuffers(0, 64, 4, 2, cuda_device)
+    ops.kmeans_assign_accum(xs0, off0, buf0)
+    assert int(buf0.cnt.sum()) == 0 and float(buf0.inertia) == 0.0

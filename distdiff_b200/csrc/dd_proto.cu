@@ -68,10 +68,10 @@ __device__ __forceinline__ int find_class(const int64_t* __restrict__ off, int C
     return lo;
 }
 
-// next batch of <= R rows of a single class, starting at the cursor
+// next batch of <= R rows of a single class, starting at the cursor.  `end` caches class_off[c+1] so the
+// common path touches no memory; only a class boundary reloads it.
 __device__ __forceinline__ void take_batch(const int64_t* __restrict__ off, int64_t r1, int R, int64_t& row, int& c,
-                                           int64_t& b_row, int& b_n, int& b_c) {
-    int64_t end = __ldg(off + c + 1);
+                                           int64_t& end, int64_t& b_row, int& b_n, int& b_c) {
     while (end <= row) { ++c; end = __ldg(off + c + 1); }
     int64_t n = end - row;
     if (n > R) n = R;
@@ -121,10 +121,11 @@ kmeans_stream_kernel(const float* __restrict__ x, const int64_t* __restrict__ cl
     int64_t irow = r0, crow = r0;
     int ic = (r0 < r1) ? find_class(class_off, C, r0) : 0;
     int cc = ic;
+    int64_t iend = (r0 < r1) ? __ldg(class_off + ic + 1) : 0, cend = iend;
     if (tid == 0) {
         for (int s = 0; s < stages && irow < r1; ++s) {
             int64_t br; int bn, bc;
-            take_batch(class_off, r1, R, irow, ic, br, bn, bc);
+            take_batch(class_off, r1, R, irow, ic, iend, br, bn, bc);
             const uint32_t bytes = (uint32_t)bn * D * sizeof(float);
             mbar_expect_tx(&full[s], bytes);
             bulk_g2s(ring + (size_t)s * stage_elems, x + br * D, bytes, &full[s]);
@@ -151,10 +152,11 @@ kmeans_stream_kernel(const float* __restrict__ x, const int64_t* __restrict__ cl
         }
     };
 
-    int it = 0, buf = 0;
+    int s = 0, buf = 0;
+    uint32_t parity = 0;
     while (crow < r1) {
         int64_t brow; int bn, bc;
-        take_batch(class_off, r1, R, crow, cc, brow, bn, bc);
+        take_batch(class_off, r1, R, crow, cc, cend, brow, bn, bc);
         if (bc != cur) {
             if (cur >= 0) flush(cur);
             cur = bc;
@@ -170,8 +172,7 @@ kmeans_stream_kernel(const float* __restrict__ x, const int64_t* __restrict__ cl
                 cnt[k] = 0;
             }
         }
-        const int s = it % stages;
-        mbar_wait(&full[s], (uint32_t)((it / stages) & 1));
+        mbar_wait(&full[s], parity);
 
         const float* st = ring + (size_t)s * stage_elems;
         float4 xv[R][PK_CH];
@@ -205,7 +206,7 @@ kmeans_stream_kernel(const float* __restrict__ x, const int64_t* __restrict__ cl
         // stage s has been read into registers by everybody: refill it
         if (tid == 0 && irow < r1) {
             int64_t br; int bn2, bc2;
-            take_batch(class_off, r1, R, irow, ic, br, bn2, bc2);
+            take_batch(class_off, r1, R, irow, ic, iend, br, bn2, bc2);
             const uint32_t bytes = (uint32_t)bn2 * D * sizeof(float);
             mbar_expect_tx(&full[s], bytes);
             bulk_g2s(ring + (size_t)s * stage_elems, x + br * D, bytes, &full[s]);
@@ -248,7 +249,7 @@ kmeans_stream_kernel(const float* __restrict__ x, const int64_t* __restrict__ cl
             }
         }
         buf ^= 1;
-        ++it;
+        if (++s == stages) { s = 0; parity ^= 1; }
     }
     if (cur >= 0) flush(cur);
     if (tid == 0) ws_inertia[g] = inert;
@@ -296,10 +297,11 @@ rownorm_stream_kernel(const float* __restrict__ feat, const int64_t* __restrict_
     int64_t irow = r0, crow = r0;
     int ic = (r0 < r1) ? find_class(class_off, C, r0) : 0;
     int cc = ic;
+    int64_t iend = (r0 < r1) ? __ldg(class_off + ic + 1) : 0, cend = iend;
     if (tid == 0) {
         for (int s = 0; s < stages && irow < r1; ++s) {
             int64_t br; int bn, bc;
-            take_batch(class_off, r1, R, irow, ic, br, bn, bc);
+            take_batch(class_off, r1, R, irow, ic, iend, br, bn, bc);
             issue(s, br, bn);
         }
     }
@@ -314,10 +316,11 @@ rownorm_stream_kernel(const float* __restrict__ feat, const int64_t* __restrict_
         if (tid == 0) ws_cnt[slot] = cnt;
     };
 
-    int it = 0, buf = 0;
+    int s = 0, buf = 0;
+    uint32_t parity = 0;
     while (crow < r1) {
         int64_t brow; int bn, bc;
-        take_batch(class_off, r1, R, crow, cc, brow, bn, bc);
+        take_batch(class_off, r1, R, crow, cc, cend, brow, bn, bc);
         if (bc != cur) {
             if (cur >= 0) flush(cur);
             cur = bc;
@@ -325,8 +328,7 @@ rownorm_stream_kernel(const float* __restrict__ feat, const int64_t* __restrict_
 #pragma unroll
             for (int ch = 0; ch < PK_CH; ++ch) acc[ch][0] = acc[ch][1] = acc[ch][2] = acc[ch][3] = 0.0;
         }
-        const int s = it % stages;
-        mbar_wait(&full[s], (uint32_t)((it / stages) & 1));
+        mbar_wait(&full[s], parity);
         const float* st = ring + (size_t)s * stage_elems;
         float4 xv[R][PK_CH];
         float v[32];
@@ -348,7 +350,7 @@ rownorm_stream_kernel(const float* __restrict__ feat, const int64_t* __restrict_
         __syncthreads();
         if (tid == 0 && irow < r1) {
             int64_t br; int bn2, bc2;
-            take_batch(class_off, r1, R, irow, ic, br, bn2, bc2);
+            take_batch(class_off, r1, R, irow, ic, iend, br, bn2, bc2);
             issue(s, br, bn2);
         }
         float tot = 0.f;
@@ -357,6 +359,9 @@ rownorm_stream_kernel(const float* __restrict__ feat, const int64_t* __restrict_
             for (int w = 0; w < PK_WARPS; ++w) tot += red[(buf * PK_WARPS + w) * 32 + lane];
         }
         const float nrm_l = sqrtf(tot);  // f.norm(dim=-1)  (dataloader.py:677)
+        float4 bs[PK_CH];  // fp32 sum of this batch's <= R rows, folded into the fp64 accumulators once per batch
+#pragma unroll
+        for (int ch = 0; ch < PK_CH; ++ch) bs[ch] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const float nrm = __shfl_sync(0xffffffffu, nrm_l, r);
@@ -368,15 +373,19 @@ rownorm_stream_kernel(const float* __restrict__ feat, const int64_t* __restrict_
                         o.x = __fdiv_rn(xv[r][ch].x, nrm); o.y = __fdiv_rn(xv[r][ch].y, nrm);
                         o.z = __fdiv_rn(xv[r][ch].z, nrm); o.w = __fdiv_rn(xv[r][ch].w, nrm);
                         *reinterpret_cast<float4*>(feat_sorted + (brow + r) * D + chunk[ch] * 4) = o;
-                        acc[ch][0] += (double)o.x; acc[ch][1] += (double)o.y;
-                        acc[ch][2] += (double)o.z; acc[ch][3] += (double)o.w;
+                        bs[ch].x += o.x; bs[ch].y += o.y; bs[ch].z += o.z; bs[ch].w += o.w;
                     }
                 }
             }
         }
+#pragma unroll
+        for (int ch = 0; ch < PK_CH; ++ch) {
+            acc[ch][0] += (double)bs[ch].x; acc[ch][1] += (double)bs[ch].y;
+            acc[ch][2] += (double)bs[ch].z; acc[ch][3] += (double)bs[ch].w;
+        }
         cnt += bn;
         buf ^= 1;
-        ++it;
+        if (++s == stages) { s = 0; parity ^= 1; }
     }
     if (cur >= 0) flush(cur);
 }
@@ -624,9 +633,8 @@ int dd_kmeans_assign_accum(const float* x_sorted, const int64_t* class_off, int6
 #define DD_KM(KK, RR, ACC) \
     case KK: rc = dd::launch_kmeans<KK, RR, ACC>(x_sorted, class_off, N, D, C, centroid, cnorm, assign, ws_sum, ws_cnt, ws_in, G, st); break;
         switch (K) {
-            DD_KM(1, 8, double) DD_KM(2, 8, double) DD_KM(3, 8, double)
-            DD_KM(4, 4, double) DD_KM(5, 4, double)
-            DD_KM(6, 4, float) DD_KM(7, 4, float)
+            DD_KM(1, 8, float) DD_KM(2, 8, float) DD_KM(3, 8, float)
+            DD_KM(4, 4, float) DD_KM(5, 4, float) DD_KM(6, 4, float) DD_KM(7, 4, float)
             DD_KM(8, 2, float) DD_KM(9, 2, float) DD_KM(10, 2, float) DD_KM(11, 2, float) DD_KM(12, 2, float)
             DD_KM(13, 2, float) DD_KM(14, 2, float) DD_KM(15, 2, float)
         }

@@ -264,7 +264,7 @@ def test_rownorm_classsum_vs_oracle(ops, cuda_device, N, C, D):
     ref = prototypes.l2_normalize_rows(feats)
     order = np.argsort(labels, kind="stable")
     assert np.array_equal(perm.cpu().numpy(), order)
-    assert np.allclose(xs.cpu().numpy(), ref[order], rtol=2e-7, atol=1e-9)
+    assert np.allclose(xs.cpu().numpy(), ref[order], rtol=1e-6, atol=1e-9)  # norm summation order: <= a few fp32 ulps
     assert np.array_equal(ccnt.cpu().numpy(), np.bincount(labels, minlength=C))
     ref_sum = np.zeros((C, D)); np.add.at(ref_sum, labels, ref.astype(np.float64))
     assert np.allclose(csum.cpu().numpy(), ref_sum, rtol=1e-6, atol=1e-7)

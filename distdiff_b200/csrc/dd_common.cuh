@@ -119,6 +119,15 @@ __device__ __forceinline__ T warp_sum(T v) {
     return v;
 }
 
+// x / d through a precomputed reciprocal + one Newton correction step (3 FMA-pipe instructions instead of the
+// ~10-instruction IEEE division sequence); returns the correctly rounded quotient except in rare
+// double-rounding corner cases (<= 1 ulp there).
+__device__ __forceinline__ float div_nr(float x, float d, float inv) {
+    const float q = x * inv;
+    const float r = fmaf(-q, d, x);
+    return fmaf(r, inv, q);
+}
+
 // Packed 2 x fp32 FMA (Blackwell FFMA2): d = a * b + c on both halves in one issue slot.
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
     unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a);

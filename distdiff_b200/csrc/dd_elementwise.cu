@@ -11,7 +11,9 @@
 namespace dd {
 
 constexpr int EW_THREADS = 256;
-constexpr int EW_UNROLL = 4;
+// independent 16-byte vectors in flight per thread: 4 for fp32; 2 for 16-bit storage (8 elements per vector,
+// so the same 64 fp32 values of register state per input and the same occupancy)
+template <typename T> constexpr int ew_unroll() { return sizeof(T) == 4 ? 4 : 2; }
 
 struct DdimScalars {
     float s;     // guidance_scale
@@ -20,12 +22,17 @@ struct DdimScalars {
     float sa_p;  // sqrt(abar_prev)
     float sb_p;  // sqrt(1 - abar_prev)
     float rho;
+    float inv_sa_t;  // 1 / sqrt(abar_t)
 };
 
+// EXACT_DIV (fp32 storage): IEEE division, bit-identical to the reference's fp32 op sequence.  16-bit storage:
+// reciprocal + Newton correction (the result is rounded to 8/11 bits right after, so the cheaper sequence is free).
+template <bool EXACT_DIV>
 __device__ __forceinline__ void ddim_math(float u, float t, float x, float g, const DdimScalars& c, bool has_text,
                                           bool has_grad, float& prev, float& x0) {
     float eps = has_text ? __fadd_rn(u, __fmul_rn(c.s, __fsub_rn(t, u))) : u;        // generate_data.py:117
-    x0 = __fdiv_rn(__fsub_rn(x, __fmul_rn(c.sb_t, eps)), c.sa_t);                     // pred_original_sample
+    const float num = __fsub_rn(x, __fmul_rn(c.sb_t, eps));
+    x0 = EXACT_DIV ? __fdiv_rn(num, c.sa_t) : div_nr(num, c.sa_t, c.inv_sa_t);        // pred_original_sample
     prev = __fadd_rn(__fmul_rn(c.sa_p, x0), __fmul_rn(c.sb_p, eps));                  // prev_sample (eta = 0)
     if (has_grad) prev = __fsub_rn(prev, __fmul_rn(c.rho, g));                        // generate_data.py:762
 }
@@ -35,6 +42,7 @@ __global__ void __launch_bounds__(EW_THREADS)
 cfg_ddim_fwd_vec(const T* __restrict__ nu, const T* __restrict__ nt, const T* __restrict__ x,
                  const T* __restrict__ grad, T* __restrict__ x_prev, T* __restrict__ x0, int64_t nvec, DdimScalars c) {
     using V = Vec16<T>;
+    constexpr int EW_UNROLL = ew_unroll<T>();
     const int64_t base = (int64_t)blockIdx.x * (EW_THREADS * EW_UNROLL) + threadIdx.x;
     V a[EW_UNROLL], b[EW_UNROLL], xx[EW_UNROLL], gg[EW_UNROLL];
 #pragma unroll
@@ -54,7 +62,7 @@ cfg_ddim_fwd_vec(const T* __restrict__ nu, const T* __restrict__ nt, const T* __
             V p, o;
 #pragma unroll
             for (int e = 0; e < V::N; ++e)
-                ddim_math(a[j].v[e], HAS_TEXT ? b[j].v[e] : 0.f, xx[j].v[e], HAS_GRAD ? gg[j].v[e] : 0.f, c, HAS_TEXT,
+                ddim_math<sizeof(T) == 4>(a[j].v[e], HAS_TEXT ? b[j].v[e] : 0.f, xx[j].v[e], HAS_GRAD ? gg[j].v[e] : 0.f, c, HAS_TEXT,
                           HAS_GRAD, p.v[e], o.v[e]);
             if (x_prev) p.store(x_prev + i * V::N);
             if (x0) o.store(x0 + i * V::N);
@@ -68,7 +76,7 @@ __global__ void cfg_ddim_fwd_scalar(const T* nu, const T* nt, const T* x, const 
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float p, o;
-    ddim_math(to_f32(nu[i]), nt ? to_f32(nt[i]) : 0.f, to_f32(x[i]), grad ? to_f32(grad[i]) : 0.f, c, nt != nullptr,
+    ddim_math<sizeof(T) == 4>(to_f32(nu[i]), nt ? to_f32(nt[i]) : 0.f, to_f32(x[i]), grad ? to_f32(grad[i]) : 0.f, c, nt != nullptr,
               grad != nullptr, p, o);
     if (x_prev) x_prev[i] = from_f32<T>(p);
     if (x0) x0[i] = from_f32<T>(o);
@@ -79,8 +87,8 @@ __global__ void cfg_ddim_fwd_scalar(const T* nu, const T* nt, const T* x, const 
 __device__ __forceinline__ void ddim_bwd_math(float gp, float g0, const DdimScalars& c, bool has_text, float& gu,
                                               float& gt, float& gx) {
     const float g0t = fmaf(c.sa_p, gp, g0);
-    const float geps = fmaf(-__fdiv_rn(c.sb_t, c.sa_t), g0t, c.sb_p * gp);
-    gx = __fdiv_rn(g0t, c.sa_t);
+    const float geps = fmaf(-(c.sb_t * c.inv_sa_t), g0t, c.sb_p * gp);
+    gx = g0t * c.inv_sa_t;
     if (has_text) {
         gu = (1.f - c.s) * geps;
         gt = c.s * geps;
@@ -95,6 +103,7 @@ __global__ void __launch_bounds__(EW_THREADS)
 cfg_ddim_bwd_vec(const T* __restrict__ g_prev, const T* __restrict__ g_x0, T* __restrict__ g_u, T* __restrict__ g_t,
                  T* __restrict__ g_x, int64_t nvec, DdimScalars c, int has_text) {
     using V = Vec16<T>;
+    constexpr int EW_UNROLL = ew_unroll<T>();
     const int64_t base = (int64_t)blockIdx.x * (EW_THREADS * EW_UNROLL) + threadIdx.x;
     V a[EW_UNROLL], b[EW_UNROLL];
 #pragma unroll
@@ -150,6 +159,7 @@ __global__ void __launch_bounds__(EW_THREADS)
 affine_project_vec(const T* __restrict__ x, const float* __restrict__ a, const float* __restrict__ b,
                    const T* __restrict__ center, T* __restrict__ y, int64_t hw_vec, int64_t HW, float radius) {
     using V = Vec16<T>;
+    constexpr int EW_UNROLL = ew_unroll<T>();
     const int64_t row = blockIdx.y;
     const float a1 = __fadd_rn(1.f, a[row]);
     const float bb = b[row];
@@ -197,6 +207,7 @@ __global__ void __launch_bounds__(EW_THREADS)
 affine_bwd_kernel(const T* __restrict__ g, const T* __restrict__ x, const float* __restrict__ a, float* __restrict__ g_a,
                   float* __restrict__ g_b, T* __restrict__ g_x, int64_t HW) {
     using V = Vec16<T>;
+    constexpr int EW_UNROLL = ew_unroll<T>();
     const int64_t row = blockIdx.x;
     const T* gr = g + row * HW;
     const T* xr = x + row * HW;
@@ -248,6 +259,7 @@ template <typename T>
 __global__ void __launch_bounds__(EW_THREADS)
 add_noise_vec(const T* __restrict__ x, const T* __restrict__ noise, T* __restrict__ out, int64_t nvec, float sa, float sb) {
     using V = Vec16<T>;
+    constexpr int EW_UNROLL = ew_unroll<T>();
     const int64_t base = (int64_t)blockIdx.x * (EW_THREADS * EW_UNROLL) + threadIdx.x;
     V a[EW_UNROLL], b[EW_UNROLL];
 #pragma unroll
@@ -273,8 +285,8 @@ __global__ void add_noise_scalar(const T* x, const T* noise, T* out, int64_t n, 
 }
 
 // ---- host-side dispatch -----------------------------------------------------------------------------
-static inline unsigned vec_blocks(int64_t nvec) {
-    return (unsigned)((nvec + EW_THREADS * EW_UNROLL - 1) / (EW_THREADS * EW_UNROLL));
+static inline unsigned vec_blocks(int64_t nvec, int unroll) {
+    return (unsigned)((nvec + EW_THREADS * unroll - 1) / (EW_THREADS * unroll));
 }
 static inline DdimScalars make_scalars(float s, float a_t, float a_prev, float rho) {
     DdimScalars c;
@@ -284,6 +296,7 @@ static inline DdimScalars make_scalars(float s, float a_t, float a_prev, float r
     c.sa_p = sqrtf(a_prev);
     c.sb_p = sqrtf(1.0f - a_prev);
     c.rho = rho;
+    c.inv_sa_t = 1.0f / c.sa_t;
     return c;
 }
 
@@ -291,13 +304,14 @@ template <typename T>
 static int cfg_ddim_fwd_t(const void* nu, const void* nt, const void* x, int64_t n, const DdimScalars& c, const void* grad,
                           void* x_prev, void* x0, cudaStream_t st) {
     using V = Vec16<T>;
+    constexpr int EW_UNROLL = ew_unroll<T>();
     const T *pnu = (const T*)nu, *pnt = (const T*)nt, *px = (const T*)x, *pg = (const T*)grad;
     T *pp = (T*)x_prev, *p0 = (T*)x0;
     const bool vec = (n % V::N == 0) && aligned16(nu) && aligned16(nt) && aligned16(x) && aligned16(grad) &&
                      aligned16(x_prev) && aligned16(x0);
     if (vec) {
         const int64_t nvec = n / V::N;
-        const unsigned grid = vec_blocks(nvec);
+        const unsigned grid = vec_blocks(nvec, EW_UNROLL);
         if (nt && grad) cfg_ddim_fwd_vec<T, true, true><<<grid, EW_THREADS, 0, st>>>(pnu, pnt, px, pg, pp, p0, nvec, c);
         else if (nt) cfg_ddim_fwd_vec<T, true, false><<<grid, EW_THREADS, 0, st>>>(pnu, pnt, px, pg, pp, p0, nvec, c);
         else if (grad) cfg_ddim_fwd_vec<T, false, true><<<grid, EW_THREADS, 0, st>>>(pnu, pnt, px, pg, pp, p0, nvec, c);
@@ -313,10 +327,11 @@ template <typename T>
 static int cfg_ddim_bwd_t(const void* g_prev, const void* g_x0, int64_t n, const DdimScalars& c, int has_text, void* g_u,
                           void* g_t, void* g_x, cudaStream_t st) {
     using V = Vec16<T>;
+    constexpr int EW_UNROLL = ew_unroll<T>();
     const bool vec = (n % V::N == 0) && aligned16(g_prev) && aligned16(g_x0) && aligned16(g_u) && aligned16(g_t) &&
                      aligned16(g_x);
     if (vec)
-        cfg_ddim_bwd_vec<T><<<vec_blocks(n / V::N), EW_THREADS, 0, st>>>((const T*)g_prev, (const T*)g_x0, (T*)g_u,
+        cfg_ddim_bwd_vec<T><<<vec_blocks(n / V::N, EW_UNROLL), EW_THREADS, 0, st>>>((const T*)g_prev, (const T*)g_x0, (T*)g_u,
                                                                         (T*)g_t, (T*)g_x, n / V::N, c, has_text);
     else
         cfg_ddim_bwd_scalar<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const T*)g_prev, (const T*)g_x0, (T*)g_u,
@@ -329,9 +344,10 @@ template <typename T>
 static int affine_fwd_t(const void* x, const float* a, const float* b, const void* center, int64_t BC, int64_t HW,
                         float radius, void* y, cudaStream_t st) {
     using V = Vec16<T>;
+    constexpr int EW_UNROLL = ew_unroll<T>();
     const bool vec = (HW % V::N == 0) && aligned16(x) && aligned16(center) && aligned16(y);
     if (vec) {
-        dim3 grid(vec_blocks(HW / V::N), (unsigned)BC);
+        dim3 grid(vec_blocks(HW / V::N, EW_UNROLL), (unsigned)BC);
         affine_project_vec<T><<<grid, EW_THREADS, 0, st>>>((const T*)x, a, b, (const T*)center, (T*)y, HW / V::N, HW, radius);
     } else {
         dim3 grid((unsigned)((HW + 255) / 256), (unsigned)BC);
@@ -345,6 +361,7 @@ template <typename T>
 static int affine_bwd_t(const void* g, const void* x, const float* a, int64_t BC, int64_t HW, float* g_a, float* g_b,
                         void* g_x, cudaStream_t st) {
     using V = Vec16<T>;
+    constexpr int EW_UNROLL = ew_unroll<T>();
     const bool vec = (HW % V::N == 0) && aligned16(g) && aligned16(x) && aligned16(g_x);
     if (vec)
         affine_bwd_kernel<T, true><<<(unsigned)BC, EW_THREADS, 0, st>>>((const T*)g, (const T*)x, a, g_a, g_b, (T*)g_x, HW);
@@ -357,9 +374,10 @@ static int affine_bwd_t(const void* g, const void* x, const float* a, int64_t BC
 template <typename T>
 static int add_noise_t(const void* x, const void* noise, int64_t n, float a_t, void* out, cudaStream_t st) {
     using V = Vec16<T>;
+    constexpr int EW_UNROLL = ew_unroll<T>();
     const float sa = sqrtf(a_t), sb = sqrtf(1.0f - a_t);
     if ((n % V::N == 0) && aligned16(x) && aligned16(noise) && aligned16(out))
-        add_noise_vec<T><<<vec_blocks(n / V::N), EW_THREADS, 0, st>>>((const T*)x, (const T*)noise, (T*)out, n / V::N, sa, sb);
+        add_noise_vec<T><<<vec_blocks(n / V::N, EW_UNROLL), EW_THREADS, 0, st>>>((const T*)x, (const T*)noise, (T*)out, n / V::N, sa, sb);
     else
         add_noise_scalar<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const T*)x, (const T*)noise, (T*)out, n, sa, sb);
     DD_LAUNCH_OK();

@@ -41,7 +41,7 @@ __device__ __forceinline__ void group_sum(float (&v)[NV], float* red /* [NV][8] 
 
 // CH = float4 chunks of the row held per thread (D <= CH * 4 * GROUP)
 template <int GROUP, int CH, int KMAX>
-__global__ void __launch_bounds__(EN_THREADS)
+__global__ void __launch_bounds__(EN_THREADS, GROUP == 32 ? 2 : 1)
 energy_kernel(const float* __restrict__ f, const int64_t* __restrict__ target, const float* __restrict__ g,
               const float* __restrict__ l, int B, int D, int C, int K, float gs, float ls, int normalize_f,
               float* __restrict__ score, float* __restrict__ per_sample, int32_t* __restrict__ kstar_out,

@@ -52,10 +52,10 @@ __device__ __forceinline__ void xreduce(float (&v)[32], int lane) {
     }
 }
 
-__device__ __forceinline__ float dot4(const float4& a, const float4& b, float acc) {
-    float2 s = ffma2(make_float2(a.x, a.y), make_float2(b.x, b.y), make_float2(acc, 0.f));
-    s = ffma2(make_float2(a.z, a.w), make_float2(b.z, b.w), s);
-    return s.x + s.y;
+// two packed FMAs per float4; the two halves of the accumulator are added once, by the caller
+__device__ __forceinline__ float2 dot4(const float4& a, const float4& b, float2 acc) {
+    acc = ffma2(make_float2(a.x, a.y), make_float2(b.x, b.y), acc);
+    return ffma2(make_float2(a.z, a.w), make_float2(b.z, b.w), acc);
 }
 
 // largest c with off[c] <= row  (=> off[c+1] > row because off[C] = N > row)
@@ -190,15 +190,15 @@ kmeans_stream_kernel(const float* __restrict__ x, const int64_t* __restrict__ cl
         for (int r = 0; r < R; ++r) {
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                float a = 0.f;
+                float2 a = make_float2(0.f, 0.f);
 #pragma unroll
                 for (int ch = 0; ch < PK_CH; ++ch) a = dot4(xv[r][ch], mu[k][ch], a);
-                v[r * (K + 1) + k] = a;
+                v[r * (K + 1) + k] = a.x + a.y;
             }
-            float a = 0.f;
+            float2 a = make_float2(0.f, 0.f);
 #pragma unroll
             for (int ch = 0; ch < PK_CH; ++ch) a = dot4(xv[r][ch], xv[r][ch], a);
-            v[r * (K + 1) + K] = a;
+            v[r * (K + 1) + K] = a.x + a.y;
         }
         xreduce<P, 16>(v, lane);
         if ((lane & (32 / P - 1)) == 0) red[(buf * PK_WARPS + warp) * 32 + (lane >> (5 - log2i(P)))] = v[0];
@@ -259,7 +259,7 @@ kmeans_stream_kernel(const float* __restrict__ x, const int64_t* __restrict__ cl
 // K1: gather by perm, L2-normalise, write class-sorted copy, per-class partial sums
 // ---------------------------------------------------------------------------------------------------
 template <int R>
-__global__ void __launch_bounds__(PK_THREADS, 1)
+__global__ void __launch_bounds__(PK_THREADS, 2)
 rownorm_stream_kernel(const float* __restrict__ feat, const int64_t* __restrict__ perm, const int64_t* __restrict__ class_off,
                       int64_t N, int D, int C, float* __restrict__ feat_sorted, double* __restrict__ ws_sum,
                       int64_t* __restrict__ ws_cnt, int stages) {
@@ -336,14 +336,14 @@ rownorm_stream_kernel(const float* __restrict__ feat, const int64_t* __restrict_
         for (int i = 0; i < 32; ++i) v[i] = 0.f;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            float a = 0.f;
+            float2 a = make_float2(0.f, 0.f);
 #pragma unroll
             for (int ch = 0; ch < PK_CH; ++ch) {
                 xv[r][ch] = own[ch] ? *reinterpret_cast<const float4*>(st + (size_t)r * D + chunk[ch] * 4)
                                     : make_float4(0.f, 0.f, 0.f, 0.f);
                 a = dot4(xv[r][ch], xv[r][ch], a);
             }
-            v[r] = a;
+            v[r] = a.x + a.y;
         }
         xreduce<P, 16>(v, lane);
         if ((lane & (32 / P - 1)) == 0) red[(buf * PK_WARPS + warp) * 32 + (lane >> (5 - log2i(P)))] = v[0];
@@ -365,13 +365,14 @@ rownorm_stream_kernel(const float* __restrict__ feat, const int64_t* __restrict_
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const float nrm = __shfl_sync(0xffffffffu, nrm_l, r);
+            const float inv = __frcp_rn(nrm);
             if (r < bn) {
 #pragma unroll
                 for (int ch = 0; ch < PK_CH; ++ch) {
                     if (own[ch]) {
                         float4 o;
-                        o.x = __fdiv_rn(xv[r][ch].x, nrm); o.y = __fdiv_rn(xv[r][ch].y, nrm);
-                        o.z = __fdiv_rn(xv[r][ch].z, nrm); o.w = __fdiv_rn(xv[r][ch].w, nrm);
+                        o.x = div_nr(xv[r][ch].x, nrm, inv); o.y = div_nr(xv[r][ch].y, nrm, inv);
+                        o.z = div_nr(xv[r][ch].z, nrm, inv); o.w = div_nr(xv[r][ch].w, nrm, inv);
                         *reinterpret_cast<float4*>(feat_sorted + (brow + r) * D + chunk[ch] * 4) = o;
                         bs[ch].x += o.x; bs[ch].y += o.y; bs[ch].z += o.z; bs[ch].w += o.w;
                     }
@@ -404,14 +405,21 @@ partial_reduce_kernel(const double* __restrict__ ws_sum, const int64_t* __restri
         g_lo = (int)(((lo + 1) * G - 1) / N);
         g_hi = (int)((hi * G - 1) / N);
     }
+    // a CTA contributes iff its (possibly empty, when N < G) row range intersects the class
+    auto hits = [&](int g) {
+        const int64_t a = N * g / G, b = N * (g + 1) / G;
+        return (a > lo ? a : lo) < (b < hi ? b : hi);
+    };
     for (int col = threadIdx.x; col < D; col += PK_THREADS) {
         double s = 0.0;
-        for (int g = g_lo; g <= g_hi; ++g) s += ws_sum[(((int64_t)g + c) * K + k) * D + col];
+        for (int g = g_lo; g <= g_hi; ++g)
+            if (hits(g)) s += ws_sum[(((int64_t)g + c) * K + k) * D + col];
         sum[((int64_t)c * K + k) * D + col] = s;
     }
     if (threadIdx.x == 0) {
         int64_t n = 0;
-        for (int g = g_lo; g <= g_hi; ++g) n += ws_cnt[((int64_t)g + c) * K + k];
+        for (int g = g_lo; g <= g_hi; ++g)
+            if (hits(g)) n += ws_cnt[((int64_t)g + c) * K + k];
         cnt[(int64_t)c * K + k] = n;
         if (blockIdx.x == 0 && inertia) {
             double t = 0.0;
@@ -513,9 +521,9 @@ static WsLayout ws_layout(int D, int C, int K, int G) {
     return w;
 }
 
-static int pick_stages(int R, int D) {
+static int pick_stages(int R, int D, size_t ring_bytes = PK_RING_BYTES) {
     const size_t stage = (size_t)R * D * sizeof(float);
-    int s = (int)(PK_RING_BYTES / stage);
+    int s = (int)(ring_bytes / stage);
     if (s > PK_MAX_STAGES) s = PK_MAX_STAGES;
     return s;
 }
@@ -543,7 +551,7 @@ extern "C" {
 
 size_t dd_proto_workspace_bytes(int D, int C, int K) {
     if (D <= 0 || C <= 0 || K <= 0) return 0;
-    return dd::ws_layout(D, C, K, dd::sm_count()).total;
+    return dd::ws_layout(D, C, K, 2 * dd::sm_count()).total;  // K1 runs 2 CTAs per SM
 }
 
 int dd_rownorm_classsum(const float* feat, const int64_t* perm, const int64_t* class_off, int64_t N, int D, int C,
@@ -555,14 +563,15 @@ int dd_rownorm_classsum(const float* feat, const int64_t* perm, const int64_t* c
                dd::PK_MAX_D);
     DD_REQUIRE(dd::aligned16(feat) && dd::aligned16(feat_sorted) && dd::aligned16(ws), DD_EINVAL,
                "dd_rownorm_classsum: feat / feat_sorted / ws must be 16-byte aligned");
-    const int G = dd::sm_count();
+    const int G = 2 * dd::sm_count();  // 2 resident CTAs per SM (90 registers, 96 KB ring each)
     const dd::WsLayout w = dd::ws_layout(D, C, 1, G);
     DD_REQUIRE(ws_bytes >= w.total, DD_EWORKSPACE, "dd_rownorm_classsum: workspace %zu < %zu bytes", ws_bytes, w.total);
     cudaStream_t st = (cudaStream_t)stream;
     double* ws_sum = (double*)((char*)ws + w.sum_off);
     int64_t* ws_cnt = (int64_t*)((char*)ws + w.cnt_off);
     constexpr int R = 4;
-    const int stages = dd::pick_stages(R, D);
+    const int stages = dd::pick_stages(R, D, 96 * 1024);
+    DD_REQUIRE(stages >= 2, DD_EUNSUPPORTED, "dd_rownorm_classsum: D=%d too large for the shared-memory ring", D);
     const size_t smem = dd::smem_bytes(stages, R, D);
     auto kern = dd::rownorm_stream_kernel<R>;
     DD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -557,7 +557,8 @@ size_t dd_proto_workspace_bytes(int D, int C, int K) {
 int dd_rownorm_classsum(const float* feat, const int64_t* perm, const int64_t* class_off, int64_t N, int D, int C,
                         float* feat_sorted, double* class_sum, int64_t* class_cnt, void* ws, size_t ws_bytes,
                         dd_stream_t stream) {
-    DD_REQUIRE(feat && class_off && feat_sorted && class_sum && class_cnt && ws, DD_EINVAL, "dd_rownorm_classsum: null pointer");
+    DD_REQUIRE((feat || N == 0) && class_off && (feat_sorted || N == 0) && class_sum && class_cnt && ws, DD_EINVAL,
+               "dd_rownorm_classsum: null pointer");
     DD_REQUIRE(N >= 0 && D >= 4 && C >= 1, DD_EINVAL, "dd_rownorm_classsum: bad sizes N=%lld D=%d C=%d", (long long)N, D, C);
     DD_REQUIRE(D % 4 == 0 && D <= dd::PK_MAX_D, DD_EUNSUPPORTED, "dd_rownorm_classsum: D=%d must be a multiple of 4 and <= %d", D,
                dd::PK_MAX_D);
@@ -622,7 +623,7 @@ int dd_kmeans_update(const double* sum, const int64_t* cnt, int C, int K, int D,
 int dd_kmeans_assign_accum(const float* x_sorted, const int64_t* class_off, int64_t N, int D, int C, int K,
                            const float* centroid, const float* cnorm, int32_t* assign, double* sum, int64_t* cnt,
                            double* inertia, void* ws, size_t ws_bytes, dd_stream_t stream) {
-    DD_REQUIRE(x_sorted && class_off && centroid && cnorm && assign && sum && cnt && ws, DD_EINVAL,
+    DD_REQUIRE((x_sorted || N == 0) && class_off && centroid && cnorm && (assign || N == 0) && sum && cnt && ws, DD_EINVAL,
                "dd_kmeans_assign_accum: null pointer");
     DD_REQUIRE(N >= 0 && D >= 4 && C >= 1, DD_EINVAL, "dd_kmeans_assign_accum: bad sizes N=%lld D=%d C=%d", (long long)N, D, C);
     DD_REQUIRE(K >= 1 && K <= 15, DD_EUNSUPPORTED, "dd_kmeans_assign_accum: K=%d outside 1..15", K);

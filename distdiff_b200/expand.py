@@ -1,0 +1,153 @@
+"""The expansion engine: the body of generate_data.py:main (reference lines 1100-1236) around the kernels.
+
+``Expander.expand_batch(batch, image_i)`` is one pass of the reference's inner loop (:1145-1227): noise at
+t_enc, the guided / unguided denoise steps, the final VAE decode and de-normalisation.  The per-step control
+flow (which step is guided, literal timestep-index arithmetic) is the reference's; the tensor math between the
+network calls is the fused kernels (guidance.py).  Optionally the unguided step (UNet forward + K5) is
+captured once in a CUDA graph and replayed -- at the reference's batch sizes that step is launch-bound.
+"""
+from __future__ import annotations
+
+import logging
+import math
+import os
+import random
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import guidance, ops, prototypes
+from .scheduler import DDIMScheduler, retrieve_timesteps
+
+logger = logging.getLogger("distdiff_b200")
+
+NUM_INFERENCE_STEPS = 50  # hard-coded in the reference (generate_data.py:1043); --steps is unused there too
+
+
+def set_seed(seed: int) -> None:
+    """accelerate.utils.set_seed (generate_data.py:861): python, numpy, torch CPU + CUDA."""
+    random.seed(seed)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    torch.cuda.manual_seed_all(seed)
+
+
+class _GraphedStep:
+    """UNet forward + K5 for one (timestep, batch shape) captured in a CUDA graph."""
+
+    def __init__(self, expander, latents, prompt_embeds, t):
+        self.static_lat = latents.clone()
+        self.static_prompt = prompt_embeds.clone()
+        self.graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(2):  # warm-up outside capture (cuDNN autotune, workspace allocation)
+                expander._step_eager(self.static_lat, self.static_prompt, t)
+        torch.cuda.current_stream().wait_stream(side)
+        with torch.cuda.graph(self.graph), torch.no_grad():
+            self.out_prev, self.out_x0 = expander._step_eager(self.static_lat, self.static_prompt, t)
+
+    def __call__(self, latents, prompt_embeds):
+        self.static_lat.copy_(latents)
+        self.static_prompt.copy_(prompt_embeds)
+        self.graph.replay()
+        return self.out_prev.clone(), self.out_x0
+
+
+class Expander:
+    def __init__(self, args, unet, vae, image_encoder, image_processor, noise_scheduler: DDIMScheduler,
+                 total_global_proto, total_local_proto, weight_dtype=torch.float16, device="cuda", use_cuda_graph=False):
+        self.args = args
+        guidance.set_args(args)
+        self.unet, self.vae, self.image_encoder, self.image_processor = unet, vae, image_encoder, image_processor
+        self.sched = noise_scheduler
+        self.gproto, self.lproto = total_global_proto, total_local_proto
+        self.weight_dtype = weight_dtype
+        self.device = torch.device(device)
+        self.timesteps, _ = retrieve_timesteps(noise_scheduler, NUM_INFERENCE_STEPS, "cpu")   # :1043-1044
+        self.use_cuda_graph = use_cuda_graph
+        self._graphs = {}
+
+    # ---- one unguided step ----
+    def _step_eager(self, latents, prompt_embeds, t):
+        return guidance.denoise_one_step(latents, self.sched, t, self.unet, prompt_embeds, None)
+
+    def _step(self, latents, prompt_embeds, t):
+        if not self.use_cuda_graph:
+            with torch.no_grad():
+                return self._step_eager(latents, prompt_embeds, t)
+        key = (int(t), tuple(latents.shape), latents.dtype)
+        g = self._graphs.get(key)
+        if g is None:
+            g = self._graphs[key] = _GraphedStep(self, latents, prompt_embeds, t)
+        return g(latents, prompt_embeds)
+
+    def expand_batch(self, batch, image_i: int = 0, decode: bool = True):
+        """generate_data.py:1145-1227 for one batch -> (images [B,3,H,W] in [0,1] or None, latents, info)."""
+        a = self.args
+        dev, wd = self.device, self.weight_dtype
+        prompt_embeds = batch["input_ids"].to(dev, dtype=wd, non_blocking=True)
+        negative_prompt_embeds = batch["uncond_inputs_ids"].to(dev, dtype=wd, non_blocking=True)
+        timesteps = self.timesteps
+        model_input = batch["image_latents"].to(dev, dtype=wd, non_blocking=True)
+        noise = torch.randn_like(model_input)                                              # :1170 (CUDA default gen)
+        start_index = guidance.start_index(a.strength, len(timesteps))                     # :1174
+        t_enc = timesteps[start_index]
+        noisy_model_input = self.sched.add_noise(model_input, noise, t_enc)                # :1176 (K7)
+        guide_ts = guidance.guide_timesteps(timesteps, a.guidance_step, a.guidance_period)  # :1178-1180
+        if a.do_classifier_free_guidance:
+            prompt_embeds = torch.cat([negative_prompt_embeds, prompt_embeds])             # :1184
+        generator = None if a.seed is None else torch.Generator(device=dev).manual_seed(a.seed)
+        latents = noisy_model_input
+        info = {"guide_timesteps": guide_ts, "scores": []}
+        logger.info("Guidance timesteps: %s", ", ".join(str(x) for x in guide_ts))
+        for t in timesteps[start_index:]:                                                  # :1199
+            if t == guide_ts[0] and a.guidance_type == "transform_guidance":
+                latents, score = guidance.transform_guidance(latents, batch, guide_ts, self.sched, self.unet, prompt_embeds,
+                                                             None, self.vae, self.image_encoder, self.image_processor, wd,
+                                                             generator, self.gproto, self.lproto)
+                latents, x_0 = self._step(latents, prompt_embeds, t)
+                info["scores"].append(score)       # no .item(): the reference syncs here every guided step (:1208)
+            elif int(t) in guide_ts and a.guidance_type == "direct_guidance":
+                latents, x_0, score = guidance.direct_guidance(latents, batch, t, self.sched, self.unet, prompt_embeds, None,
+                                                               self.vae, self.image_encoder, self.image_processor, wd,
+                                                               generator, self.gproto, self.lproto)
+                info["scores"].append(score)
+            else:
+                latents, x_0 = self._step(latents, prompt_embeds, t)
+        image = None
+        if decode:
+            with torch.no_grad():                                                          # :1221-1227
+                image = self.vae.decode(latents / self.vae.config.scaling_factor, return_dict=False, generator=generator)[0]
+                image = self.image_processor.postprocess(image, output_type="pt", do_denormalize=[True] * image.shape[0])
+        return image, latents, info
+
+
+def output_path(args, batch, i, image_i) -> str:
+    """generate_data.py:1134-1135 / 1231-1232."""
+    image_file_path = os.path.basename(batch["image_paths"][i]).split(".")[0]
+    return f'{args.output_dir}/{batch["class_names"][i]}/{image_file_path}_expand_{image_i}.png'
+
+
+def run_expansion(args, expander: Expander, train_dataloader, save: bool = True):
+    """generate_data.py:1130-1236: batches x image_i with skip-if-exists resume."""
+    from torchvision.utils import save_image
+    n_done = 0
+    for _step, batch in enumerate(train_dataloader):
+        for image_i in range(args.first_image_index, args.num_images_per_prompt):
+            paths = [output_path(args, batch, i, image_i) for i in range(len(batch["image_paths"]))]
+            if save and all(os.path.exists(p) for p in paths):                             # :1132-1143
+                for p in paths:
+                    print(f"File {p} exists, so skipped.")
+                continue
+            image, _lat, info = expander.expand_batch(batch, image_i)
+            for s, t in zip(info["scores"], info["guide_timesteps"]):
+                logger.info("%s in %s step for %s steps period, score: %.4f", args.guidance_type, t, args.guidance_period, float(s))
+            if save:
+                for i, p in enumerate(paths):
+                    os.makedirs(os.path.dirname(p), exist_ok=True)
+                    save_image([image[i]], p)
+            n_done += len(paths)
+    return n_done

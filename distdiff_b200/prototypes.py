@@ -1,0 +1,252 @@
+"""Drop-in mirror of the reference's prototype construction (dataloader.py:664-747, generate_data.py:1104-1127).
+
+``extract_prototype(args, train_loader, model)`` and ``extract_prototypes_with_encoder(args, model)`` keep the
+reference's signatures and return the same ``(np.float32 [C,D], np.float32 [C,K,D])`` pair.  Underneath:
+
+* the guide features never leave the GPU (the reference D2H-copies every batch and gathers per class in
+  python lists, dataloader.py:678-697);
+* K1 normalises the rows, writes them class-sorted and produces the class sums in one pass; K2 turns sums
+  into means;
+* the group prototypes come from K3' (average-linkage agglomerative, the reference's algorithm and the
+  default) or K3 (per-class Lloyd k-means, ``--cluster_method kmeans``, the north-star extension);
+* with ``world > 1`` the samples are sharded per GPU and class / centroid sums are all-reduced over NCCL;
+  agglomerative clustering shards by class (every class is an independent problem).
+
+The prototype file layout the reference left commented out (dataloader.py:725-727) is enabled:
+``./save/prototypes/{arch}/{dataset}/class_wise_prototype_K{K}.npz`` with ``global_prototypes`` /
+``local_prototypes`` -- computed once, reused by every split process.
+"""
+from __future__ import annotations
+
+import os
+from typing import Callable, Optional
+
+import numpy as np
+import torch
+
+from . import ops
+from ._lib import DistDiffError
+
+
+class Collective:
+    """What the sharded prototype stage needs from the communication layer."""
+
+    rank = 0
+    world = 1
+
+    def allreduce(self, sum_: Optional[torch.Tensor], cnt: Optional[torch.Tensor]) -> None:  # in place, SUM
+        return None
+
+    def allgather_rows(self, t: torch.Tensor) -> torch.Tensor:  # concat along dim 0 in rank order (ragged ok)
+        return t
+
+
+class NcclCollective(Collective):
+    """NCCL through the C ABI (dd_comm_*) for the per-iteration all-reduce; torch.distributed (same NCCL) for
+    the one-off ragged all-gather.  Requires torch.distributed to be initialised (torchrun)."""
+
+    def __init__(self):
+        import torch.distributed as dist
+        self.dist = dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+
+        def exchange(uid: bytes) -> bytes:
+            box = [uid]
+            dist.broadcast_object_list(box, src=0)
+            return box[0]
+
+        self.comm = ops.Comm(self.rank, self.world, exchange)
+
+    def allreduce(self, sum_, cnt):
+        self.comm.allreduce(sum_, cnt)
+
+    def allgather_rows(self, t):
+        n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+        sizes = [torch.zeros_like(n) for _ in range(self.world)]
+        self.dist.all_gather(sizes, n)
+        sizes = [int(s) for s in sizes]
+        mx = max(sizes)
+        pad = torch.zeros((mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        pad[: t.shape[0]] = t
+        out = [torch.empty_like(pad) for _ in range(self.world)]
+        self.dist.all_gather(out, pad)
+        return torch.cat([o[:s] for o, s in zip(out, sizes)], 0)
+
+
+def _class_shard(counts: np.ndarray, world: int):
+    """Contiguous class ranges balanced by sum n_c^2 (the agglomerative cost)."""
+    w = counts.astype(np.float64) ** 2 + 1.0
+    target = w.sum() / world
+    bounds, acc, r = [0], 0.0, 1
+    for c, v in enumerate(w):
+        acc += v
+        while r < world and acc >= target * r:
+            bounds.append(c + 1)
+            r += 1
+    while len(bounds) < world + 1:
+        bounds.append(len(counts))
+    bounds[-1] = len(counts)
+    return bounds
+
+
+def build_prototypes(features: torch.Tensor, labels: torch.Tensor, num_classes: int, K: int,
+                     cluster_method: str = "agglomerative", kmeans_iters: int = 20,
+                     coll: Optional[Collective] = None, return_debug: bool = False):
+    """features: [N_local, D] raw guide features (cuda fp32, dataset order); labels: [N_local] class ids.
+
+    Returns (global [C,D] f32, local [C,K,D] f32) device tensors, UN-normalised like the reference's numpy
+    arrays (the caller normalises them once for guidance, generate_data.py:1113-1127).
+    """
+    coll = coll or Collective()
+    dev = features.device
+    C_ = int(num_classes)
+    perm, off = ops.sort_by_class(labels, C_)
+    xs, csum, ccnt = ops.rownorm_classsum(features, perm, off)                 # K1
+    coll.allreduce(csum, ccnt)
+    gmean, _ = ops.class_mean(csum, ccnt, want_unit=False)                     # K2
+    counts = ccnt.cpu().numpy()                                                # one small D2H (C int64)
+    if (counts < max(K, 2 if cluster_method == "agglomerative" else 1)).any():
+        bad = int(np.argmax(counts < max(K, 2)))
+        raise ValueError(f"class {bad} has {int(counts[bad])} samples: every class needs >= max(K, 2) = {max(K, 2)} "
+                         "(sklearn AgglomerativeClustering raises the same way, dataloader.py:713)")
+    debug = {"perm": perm, "class_off": off, "x_sorted": xs}
+
+    if cluster_method == "agglomerative":                                       # K3' (reference behaviour)
+        if coll.world > 1:
+            # classes are the independent units: gather the (normalised, class-sorted) shards, re-sort globally,
+            # then every rank clusters a contiguous class range and the prototypes are all-reduced (disjoint sums)
+            lab_sorted = torch.repeat_interleave(torch.arange(C_, device=dev), (off[1:] - off[:-1]))
+            xs_all = coll.allgather_rows(xs)
+            lab_all = coll.allgather_rows(lab_sorted)
+            perm2, off2 = ops.sort_by_class(lab_all, C_)          # stable: rank order == dataset order inside a class
+            xs = xs_all[perm2].contiguous()
+            off = off2
+            bounds = _class_shard(counts, coll.world)
+            c0, c1 = bounds[coll.rank], bounds[coll.rank + 1]
+        else:
+            c0, c1 = 0, C_
+        lsum = torch.zeros(C_, K, xs.shape[1], dtype=torch.float64, device=dev)
+        lcnt = torch.zeros(C_, K, dtype=torch.int64, device=dev)
+        labels_sorted = torch.full((xs.shape[0],), -1, dtype=torch.int32, device=dev)
+        if c1 > c0:
+            lab, s, n, status = ops.agglo_average(xs, off[c0:c1 + 1].contiguous(), K, int(counts[c0:c1].max()))
+            if int(status.abs().sum()) != 0:
+                raise DistDiffError(f"agglomerative clustering failed, status={status.cpu().tolist()}")
+            lsum[c0:c1] = s
+            lcnt[c0:c1] = n
+            labels_sorted = lab
+        coll.allreduce(lsum, lcnt)
+        lmean, _ = ops.class_mean(lsum, lcnt, want_unit=False)
+        debug.update(labels_sorted=labels_sorted, x_sorted=xs, class_off=off)
+    elif cluster_method == "kmeans":                                            # K3 (north-star extension)
+        N, D = xs.shape
+        buf = ops.KMeansBuffers(N, D, C_, K, dev)
+        # seed: the floor(k*n_c/K)-th row of class c in GLOBAL dataset order; shards are contiguous blocks of the
+        # dataset, so global order inside a class = rank order, then local order
+        local_counts = (off[1:] - off[:-1])
+        if coll.world > 1:
+            allc = coll.allgather_rows(local_counts[None, :])                  # [world, C]
+            before = allc[: coll.rank].sum(0)
+        else:
+            before = torch.zeros_like(local_counts)
+        total = torch.from_numpy(counts).to(dev)
+        kk = torch.arange(K, device=dev)[None, :]
+        gpos = (kk * total[:, None]) // K                                      # [C,K] position inside the class
+        lpos = gpos - before[:, None]
+        mine = (lpos >= 0) & (lpos < local_counts[:, None])
+        row_idx = torch.where(mine, off[:-1, None] + lpos, torch.full_like(lpos, -1)).contiguous()
+        s, n = ops.kmeans_seed(xs, row_idx)
+        coll.allreduce(s, n)
+        ops.kmeans_update(s, n, buf.centroid, buf.cnorm)
+        inertia = []
+        for _ in range(int(kmeans_iters)):
+            ops.kmeans_assign_accum(xs, off, buf)                              # K3
+            coll.allreduce(buf.sum, buf.cnt)                                   # centroid sums + counts over NVLink
+            ops.kmeans_update(buf.sum, buf.cnt, buf.centroid, buf.cnorm)
+            if return_debug:
+                inertia.append(buf.inertia.clone())
+        lmean = buf.centroid
+        debug.update(labels_sorted=buf.assign, inertia=inertia, counts=buf.cnt)
+    else:
+        raise ValueError(f"unknown cluster_method {cluster_method!r} (agglomerative | kmeans)")
+    if return_debug:
+        return gmean, lmean, debug
+    return gmean, lmean
+
+
+@torch.no_grad()
+def extract_prototype(args, train_loader, model, coll: Optional[Collective] = None):
+    """dataloader.py:664-731 -> (global_prototypes np.f32 [C,D], class_sub_prototypes np.f32 [C,K,D])."""
+    model.eval()
+    feats, labels = [], []
+    dev = next(model.parameters()).device
+    if dev.type != "cuda":
+        raise DistDiffError("extract_prototype needs the guide model on a CUDA device (no CPU path)")
+    for original_inputs, targets in train_loader:
+        original_inputs = original_inputs.to(dev, non_blocking=True)
+        feats.append(model.encode_image(original_inputs).float())              # stays on the GPU
+        labels.append(torch.as_tensor(targets).to(dev))
+    features = torch.cat(feats, 0).contiguous()
+    labels = torch.cat(labels, 0)
+    num_classes = getattr(args, "num_classes", None)
+    if num_classes is None:
+        nmax = labels.max()
+        if coll is not None and coll.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(nmax, op=dist.ReduceOp.MAX)
+        num_classes = int(nmax) + 1                                            # len(set(label_list)), dataloader.py:690
+    g, l = build_prototypes(features, labels, num_classes, int(args.K),
+                            getattr(args, "cluster_method", "agglomerative"), getattr(args, "kmeans_iters", 20), coll)
+    return g.cpu().numpy(), l.cpu().numpy()
+
+
+def prototype_path(args) -> str:
+    """dataloader.py:725-727 (commented out upstream)."""
+    save_dir = "./save/prototypes/{}/{}/".format(args.arch, args.dataset)
+    return os.path.join(save_dir, f"class_wise_prototype_K{args.K}.npz")
+
+
+def extract_prototypes_with_encoder(args, model, trainset_factory: Optional[Callable] = None,
+                                    coll: Optional[Collective] = None, cache: bool = True):
+    """dataloader.py:734-747.  ``trainset_factory(args, transform)`` returns a dataset of (image, label);
+    default: distdiff_b200.data.load_trainset (Caltech-101-shaped folder or synthetic set)."""
+    from torch.utils import data as tdata
+    from torchvision import transforms
+    path = prototype_path(args)
+    method = getattr(args, "cluster_method", "agglomerative")
+    if cache and method == "agglomerative" and os.path.exists(path):
+        z = np.load(path)
+        return z["global_prototypes"], z["local_prototypes"]
+    transform = transforms.Compose([                                            # dataloader.py:736-742
+        transforms.Resize((224, 224)),
+        transforms.ToTensor(),
+        transforms.Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225]),
+    ])
+    if trainset_factory is None:
+        from .data import load_trainset as trainset_factory
+    trainset = trainset_factory(args, transform)
+    if coll is not None and coll.world > 1:                                     # contiguous dataset block per rank
+        n = len(trainset)
+        per = -(-n // coll.world)
+        idx = list(range(min(per * coll.rank, n), min(per * (coll.rank + 1), n)))
+        trainset = tdata.Subset(trainset, idx)
+    loader = tdata.DataLoader(trainset, batch_size=64, shuffle=False, drop_last=False)
+    model = model.float()
+    g, l = extract_prototype(args, loader, model, coll)
+    if cache and method == "agglomerative" and (coll is None or coll.rank == 0):
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        tmp = path + f".tmp{os.getpid()}.npz"
+        np.savez(tmp, global_prototypes=g, local_prototypes=l)
+        os.replace(tmp, path)                                                   # atomic: concurrent splits race-free
+    return g, l
+
+
+def prototypes_to_device(global_np, local_np, optimize_targets, device):
+    """generate_data.py:1112-1127 -- upload + L2-normalise rows; honours --optimize_targets parsing."""
+    total_global_proto = total_local_proto = None
+    if optimize_targets is not None:
+        if "global_prototype" in optimize_targets:
+            total_global_proto = ops.normalize_rows(torch.from_numpy(np.ascontiguousarray(global_np, np.float32)).to(device))
+        if "local_prototype" in optimize_targets:
+            total_local_proto = ops.normalize_rows(torch.from_numpy(np.ascontiguousarray(local_np, np.float32)).to(device))
+    return total_global_proto, total_local_proto

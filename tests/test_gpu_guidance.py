@@ -1,0 +1,206 @@
+"""GPU parity of the host-side mirror (distdiff_b200.guidance / prototypes / scheduler) against the golden
+vectors produced by the reference's own function bodies and against the CPU oracle.
+
+north_star tolerance: per-step latents within 1e-3 relative in fp32 (bf16 stated separately); prototypes
+within 1e-5 relative; k-means assignments identical except documented ties.
+"""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import standins
+from oracle import ddim as o_ddim
+from oracle import prototypes as o_proto
+
+pytestmark = pytest.mark.gpu
+
+GUIDE_CASES = ["guidance_small", "guidance_d2048", "guidance_b1"]
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _strict_fp32():
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def _setup(case, dev):
+    from distdiff_b200 import guidance
+    from distdiff_b200.scheduler import DDIMScheduler
+    unet, vae, enc = standins.make_nets(seed=0, feat_dim=case["feat_dim"])
+    unet.load_state_dict(case["unet"]); vae.load_state_dict(case["vae"]); enc.load_state_dict(case["enc"])
+    for m in (unet, vae, enc):
+        m.to(dev).requires_grad_(False)
+    sched = DDIMScheduler()
+    sched.set_timesteps(50)
+    guidance.set_args(types.SimpleNamespace(**case["args"]))
+    return guidance, sched, unet, vae, enc
+
+
+def _rel(a, b):
+    return float((a - b).norm() / b.norm())
+
+
+def test_scheduler_tables_match_oracle(cuda_device):
+    from distdiff_b200.scheduler import DDIMScheduler
+    s = DDIMScheduler()
+    ts = s.set_timesteps(50)
+    assert torch.equal(ts, o_ddim.timesteps(50))
+    assert torch.equal(s.alphas_cumprod, o_ddim.alphas_cumprod())
+    for t in (981, 381, 21, 1):
+        a, b = s.alpha_pair(t)
+        ra, rb = o_ddim.alpha_pair(t)
+        assert a == float(ra) and b == float(rb)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 4, 8, 8, generator=g); n = torch.randn(2, 4, 8, 8, generator=g)
+    out = s.add_noise(x.to(cuda_device), n.to(cuda_device), ts[4])
+    assert torch.equal(out.cpu(), o_ddim.add_noise(x, n, o_ddim.alphas_cumprod()[int(ts[4])]))
+    d = s.step(n.to(cuda_device), 381, x.to(cuda_device))
+    rp, r0 = o_ddim.ddim_step(n, x, *o_ddim.alpha_pair(381))
+    assert torch.equal(d["prev_sample"].cpu(), rp) and torch.equal(d["pred_original_sample"].cpu(), r0)
+
+
+@pytest.mark.parametrize("name", GUIDE_CASES)
+def test_denoise_one_step_golden(cuda_device, golden, name):
+    case = golden[name]
+    guidance, sched, unet, vae, enc = _setup(case, cuda_device)
+    with torch.no_grad():
+        prev, x0 = guidance.denoise_one_step(case["latents"].to(cuda_device), sched, case["denoise"]["t"], unet,
+                                             case["prompt_embeds"].to(cuda_device), None)
+    assert _rel(prev.cpu(), case["denoise"]["prev"]) < 1e-5      # only the UNet's GPU-vs-CPU conv rounding differs
+    assert _rel(x0.cpu(), case["denoise"]["x0"]) < 1e-5
+
+
+@pytest.mark.parametrize("name", GUIDE_CASES)
+def test_transform_guidance_golden(cuda_device, golden, name):
+    case = golden[name]
+    guidance, sched, unet, vae, enc = _setup(case, cuda_device)
+    proc = standins.IdentityProcessor()
+    for key, use_l in (("transform", True), ("transform_global_only", False)):
+        torch.manual_seed(case[key]["seed"])      # the channel noise comes from the CPU global RNG (generate_data.py:692-695)
+        lat, score = guidance.transform_guidance(case["latents"].to(cuda_device), {"targets": case["targets"]}, [381, 361],
+                                                 sched, unet, case["prompt_embeds"].to(cuda_device), None, vae, enc, proc,
+                                                 torch.float32, None, case["global_proto"].to(cuda_device),
+                                                 case["local_proto"].to(cuda_device) if use_l else None)
+        assert _rel(lat.cpu(), case[key]["latents_out"]) < 1e-3          # north_star: latents within 1e-3 rel (fp32)
+        assert abs(float(score) - case[key]["score"]) < 1e-4 * abs(case[key]["score"])
+        assert not lat.requires_grad
+
+
+@pytest.mark.parametrize("name", GUIDE_CASES)
+def test_direct_guidance_golden(cuda_device, golden, name):
+    case = golden[name]
+    guidance, sched, unet, vae, enc = _setup(case, cuda_device)
+    proc = standins.IdentityProcessor()
+    for key, use_g in (("direct", True), ("direct_local_only", False)):
+        lat, x0, score = guidance.direct_guidance(case["latents"].to(cuda_device), {"targets": case["targets"]}, 381, sched,
+                                                  unet, case["prompt_embeds"].to(cuda_device), None, vae, enc, proc,
+                                                  torch.float32, None,
+                                                  case["global_proto"].to(cuda_device) if use_g else None,
+                                                  case["local_proto"].to(cuda_device))
+        assert _rel(lat.cpu(), case[key]["latents_out"]) < 1e-3
+        assert _rel(x0.cpu(), case[key]["x0"]) < 1e-5
+        assert abs(float(score) - case[key]["score"]) < 1e-4 * abs(case[key]["score"])
+
+
+def test_guidance_bf16_runs_close(cuda_device, golden):
+    """bf16 tolerance (stated separately from the fp32 bar): latents within 5e-2 relative of the fp32 golden."""
+    case = golden["guidance_small"]
+    guidance, sched, unet, vae, enc = _setup(case, cuda_device)
+    for m in (unet, vae, enc):
+        m.to(torch.bfloat16)
+    lat, x0, score = guidance.direct_guidance(case["latents"].to(cuda_device, torch.bfloat16), {"targets": case["targets"]}, 381,
+                                              sched, unet, case["prompt_embeds"].to(cuda_device, torch.bfloat16), None, vae, enc,
+                                              standins.IdentityProcessor(), torch.bfloat16, None,
+                                              case["global_proto"].to(cuda_device), case["local_proto"].to(cuda_device))
+    assert lat.dtype == torch.bfloat16
+    assert _rel(lat.float().cpu(), case["direct"]["latents_out"]) < 5e-2
+
+
+def test_linfball_proj_golden(cuda_device, golden):
+    from distdiff_b200 import guidance
+    c = golden["linfball"]
+    t = c["t"].to(cuda_device)
+    out = guidance.linfball_proj(c["center"].to(cuda_device), c["radius"], t, in_place=True)
+    assert out is t and torch.equal(t.cpu(), c["out"])
+
+
+# ------------------------------------------------------------------------------------------------ prototypes
+@pytest.mark.parametrize("name", ["proto_caltech_like", "proto_d2048", "proto_k5"])
+def test_extract_prototype_golden(cuda_device, golden, name):
+    from distdiff_b200 import prototypes
+    c = golden[name]
+
+    class _Model(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.p = torch.nn.Parameter(torch.zeros(1))
+
+        def encode_image(self, x):
+            return x
+
+    feats, labels = c["features"], c["labels"]
+    loader = [(feats[i:i + 64], labels[i:i + 64]) for i in range(0, len(labels), 64)]
+    g, l = prototypes.extract_prototype(types.SimpleNamespace(K=c["K"]), loader, _Model().to(cuda_device))
+    rg, rl = c["global_prototypes"].numpy(), c["local_prototypes"].numpy()
+    assert g.dtype == np.float32 and l.dtype == np.float32 and g.shape == rg.shape and l.shape == rl.shape
+    assert np.abs(g - rg).max() <= 1e-5 * np.abs(rg).max() and np.allclose(g, rg, rtol=1e-5, atol=1e-8)
+    assert np.abs(l - rl).max() <= 1e-5 * np.abs(rl).max() and np.allclose(l, rl, rtol=1e-5, atol=1e-8)
+    # normalised copies used for guidance (generate_data.py:1113-1127)
+    gp, lp = prototypes.prototypes_to_device(g, l, ["global_prototype", "local_prototype"], cuda_device)
+    og, ol = o_proto.normalize_prototypes(rg, rl)
+    assert np.allclose(gp.cpu().numpy(), og, rtol=1e-5, atol=1e-8) and np.allclose(lp.cpu().numpy(), ol, rtol=1e-5, atol=1e-8)
+    gp2, lp2 = prototypes.prototypes_to_device(g, l, ["global_prototype"], cuda_device)
+    assert lp2 is None and gp2 is not None
+
+
+def test_kmeans_prototypes_vs_oracle(cuda_device):
+    """Full Lloyd runs on well-separated synthetic clusters: assignments identical, prototypes within 1e-5."""
+    from distdiff_b200 import prototypes
+    rng = np.random.default_rng(3)
+    C, K, D, per = 6, 4, 256, 120
+    centers = rng.normal(size=(C, K, D)) * 4.0
+    labels = np.repeat(np.arange(C), per); rng.shuffle(labels)
+    which = rng.integers(0, K, size=len(labels))
+    feats = (centers[labels, which] + rng.normal(size=(len(labels), D))).astype(np.float32)
+    fn = o_proto.l2_normalize_rows(feats)
+    rg, rl, rassign = o_proto.kmeans_prototypes(fn, labels.tolist(), K, iters=15)
+    g, l, dbg = prototypes.build_prototypes(torch.from_numpy(feats).to(cuda_device), torch.from_numpy(labels).to(cuda_device), C, K,
+                                            "kmeans", 15, return_debug=True)
+    assert np.allclose(g.cpu().numpy(), rg, rtol=1e-5, atol=1e-7)
+    assert np.allclose(l.cpu().numpy(), rl, rtol=1e-5, atol=1e-7)
+    off = dbg["class_off"].cpu().numpy(); a = dbg["labels_sorted"].cpu().numpy()
+    for c in range(C):
+        assert np.array_equal(a[off[c]:off[c + 1]], rassign[c])
+    inert = [float(v) for v in dbg["inertia"]]
+    assert all(inert[i + 1] <= inert[i] * (1 + 1e-6) for i in range(len(inert) - 1))   # Lloyd: monotone
+
+
+def test_kmeans_full_size_properties(cuda_device):
+    """BASELINE config 4 size (N=100k x 2048, C=100): size-independent properties instead of an oracle run --
+    counts sum to N, every assignment in range, inertia non-increasing, centroid = mean of its members."""
+    from distdiff_b200 import ops, prototypes
+    N, C, K, D = 100_000, 100, 5, 2048
+    g = torch.Generator(device=cuda_device).manual_seed(7)
+    feats = torch.randn(N, D, device=cuda_device, generator=g)
+    labels = torch.arange(N, device=cuda_device) % C
+    gm, lm, dbg = prototypes.build_prototypes(feats, labels, C, K, "kmeans", 6, return_debug=True)
+    assert int(dbg["counts"].sum()) == N
+    a = dbg["labels_sorted"]
+    assert int(a.min()) >= 0 and int(a.max()) < K
+    inert = [float(v) for v in dbg["inertia"]]
+    assert all(inert[i + 1] <= inert[i] * (1 + 1e-7) for i in range(len(inert) - 1))
+    xs, off = dbg["x_sorted"], dbg["class_off"]
+    # last update used the last assignment: recompute two classes' centroids with torch and compare
+    for c in (0, 57):
+        rows = xs[off[c]:off[c + 1]].double(); ac = a[off[c]:off[c + 1]].long()
+        ref = torch.zeros(K, D, dtype=torch.float64, device=cuda_device).index_add_(0, ac, rows)
+        cnt = torch.bincount(ac, minlength=K).clamp(min=1)[:, None]
+        assert torch.allclose(lm[c].double(), ref / cnt, rtol=1e-5, atol=1e-7)
+    # class means of unit rows: ||mean|| <= 1, and equal to a torch reference
+    ref = torch.zeros(C, D, dtype=torch.float64, device=cuda_device).index_add_(0, labels, torch.nn.functional.normalize(feats, dim=-1).double()) / (N // C)
+    assert torch.allclose(gm.double(), ref, rtol=1e-5, atol=1e-8)

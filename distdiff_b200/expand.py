@@ -39,6 +39,7 @@ class _GraphedStep:
     def __init__(self, expander, latents, prompt_embeds, t):
         self.static_lat = latents.clone()
         self.static_prompt = prompt_embeds.clone()
+        t = (int(t), torch.full((1,), int(t), dtype=torch.int64, device=latents.device))  # no H2D copy inside the capture
         self.graph = torch.cuda.CUDAGraph()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -72,7 +73,16 @@ class Expander:
 
     # ---- one unguided step ----
     def _step_eager(self, latents, prompt_embeds, t):
-        return guidance.denoise_one_step(latents, self.sched, t, self.unet, prompt_embeds, None)
+        if not isinstance(t, tuple):
+            return guidance.denoise_one_step(latents, self.sched, t, self.unet, prompt_embeds, None)
+        # graph capture: same four lines as denoise_one_step (generate_data.py:109-121) with the timestep already on
+        # the device for the UNet and as a python int for the scheduler tables
+        t_host, t_dev = t
+        cfg = bool(self.args.do_classifier_free_guidance)
+        x = torch.cat([latents] * 2) if cfg else latents
+        noise_pred = self.unet(x, t_dev, prompt_embeds, class_labels=None, return_dict=False)[0]
+        a_t, a_prev = self.sched.alpha_pair(t_host)
+        return ops.cfg_ddim_step(noise_pred, latents, float(self.args.guidance_scale), a_t, a_prev, cfg=cfg)
 
     def _step(self, latents, prompt_embeds, t):
         if not self.use_cuda_graph:

@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""bench.py -- expanded images/sec of the DistDiff guided-expansion hot path on B200 (+ kernel rooflines).
+
+    python bench.py --gpus N --steps K --warmup W            # ours (torchrun launches it for N > 1)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on host cores
+
+Workload (BASELINE.json configs[1]): Caltech-101-shaped synthetic data (100 classes),
+SD-v1.4-shaped UNet/VAE + ResNet-50 guide with random-init weights (no network), 512 px, 50 DDIM steps
+(--strength 1.0), CFG 7.5, transform_guidance at t = 381 over 2 sub-steps, K = 3 agglomerative group
+prototypes, rho 10, L-inf radius 0.2 (scripts/exps/expand_diff.sh).  One "step" = one batch of B images
+expanded once (one pass of generate_data.py:1145-1227).  Multi-GPU = the reference's image split: every rank
+expands its own images, no data-path collective ("scaling": "weak").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+import types
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "expanded images/sec"
+UNIT = "images/s"
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=3)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--batch", type=int, default=4, help="images per step and GPU (train_batch_size)")
+    p.add_argument("--dtype", default="fp16", choices=["fp16", "bf16", "fp32"], help="UNet/VAE/latent storage type (reference: fp16)")
+    p.add_argument("--no-cuda-graph", action="store_true")
+    p.add_argument("--no-kernels", action="store_true", help="skip the batched kernel micro-benchmarks")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--tiny", action="store_true", help="tiny networks (CI smoke of bench.py itself; not a valid number)")
+    return p.parse_args()
+
+
+def canonical_args(batch):
+    """scripts/exps/expand_diff.sh:3-16 with --strength 1.0 (50 DDIM steps, BASELINE configs[1])."""
+    return types.SimpleNamespace(do_classifier_free_guidance=True, guidance_scale=7.5, gs=1.0, ls=1.0, rho=10.0,
+                                 guidance_type="transform_guidance", guidance_step=20, guidance_period=2, constraint_value=0.2,
+                                 K=3, strength=1.0, seed=42, train_batch_size=batch, cluster_method="agglomerative",
+                                 num_classes=100, arch="resnet50", dataset="caltech-101")
+
+
+def workload_config(a, batch, world, graph, dtype):
+    return {"workload": "Caltech-101 5x expansion, ResNet-50 guide, SD v1.4 512px, 50 DDIM steps (BASELINE configs[1])",
+            "images_per_step_per_gpu": batch, "ddim_steps": 50, "guidance": "transform_guidance t=381 period 2",
+            "K": a.K, "cluster_method": a.cluster_method, "cfg_scale": a.guidance_scale, "latent": "4x64x64",
+            "storage_dtype": dtype, "weights": "random-init SD-v1.x UNet (859.5M) / VAE / ResNet-50",
+            "parallelism": f"image-split x{world} (no collective)", "cuda_graph_unguided_step": bool(graph),
+            "l2": "every step streams ~3.4 GB of UNet weights+activations (> 126 MB L2) between two launches of the same kernel; "
+                  "micro-benchmarks evict L2 by reading 512 MB before each timed launch"}
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = sorted(int(r[1]) for r in self.rows if len(r) > 8 and r[1].isdigit())
+        mx = [int(r[2]) for r in self.rows if len(r) > 8 and r[2].isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) > 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------- models / data
+def build_models(tiny, seed=0):
+    import torch
+    from distdiff_b200 import nets
+    torch.manual_seed(seed)
+    if tiny:
+        unet = nets.UNet2DConditionModel(block_out_channels=(32, 64, 64, 64), heads=2)
+        vae = nets.AutoencoderKL(chs=(32, 32, 64, 64), with_encoder=False)
+        guide = nets.create_model("resnet18", num_classes=100)
+    else:
+        unet = nets.UNet2DConditionModel()
+        vae = nets.AutoencoderKL(with_encoder=False)
+        guide = nets.create_model("resnet50", num_classes=100)
+    for m in (unet, vae, guide):
+        m.requires_grad_(False).eval()
+    return unet, vae, guide
+
+
+def synthetic_batch(batch, rank, step_seed=0, size=64):
+    """One batch of the Caltech-shaped workload as HOST tensors: VAE latents [B,4,64,64] (scaled like
+    latent_dist.sample()*0.18215), class prompt / unconditional embeddings [B,77,768], labels, names."""
+    import torch
+    g = torch.Generator().manual_seed(1234 + 7919 * rank + step_seed)
+    targets = [(rank * batch + i) % 100 for i in range(batch)]
+    return {"image_latents": (torch.randn(batch, 4, size, size, generator=g) * 0.18215 * 4.0),
+            "input_ids": torch.randn(batch, 77, 768, generator=g), "uncond_inputs_ids": torch.randn(1, 77, 768, generator=g).expand(batch, -1, -1).contiguous(),
+            "targets": targets, "class_names": [f"class {t:03d}" for t in targets],
+            "image_paths": [f"synthetic/class_{t:03d}/image_{rank:02d}_{i:04d}.jpg" for i, t in enumerate(targets)]}
+
+
+def synthetic_guide_features(n=3000, d=2048, c=100, seed=7):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    centers = torch.randn(c, 3, d, generator=g)
+    labels = torch.arange(n) % c
+    which = torch.randint(0, 3, (n,), generator=g)
+    return centers[labels, which] * 1.5 + torch.randn(n, d, generator=g), labels
+
+
+# ----------------------------------------------------------------------------------------------- CPU oracle arm
+def cpu_reference_sample(a, tiny, steps, warmup, log=lambda *_: None):
+    """The reference's algorithm (oracle port: CPU fp32 restatement of generate_data.py:109-137,687-732) on the host
+    cores, B = 1, full-size networks.  Bounded sample: `steps` unguided denoise steps (after `warmup`), ONE
+    transform_guidance call (2 sub-steps fwd+bwd through UNet, VAE decoder, ResNet-50) and ONE final VAE decode;
+    images/sec = 1 / (50 * t_unguided + t_guided + t_decode)."""
+    import torch
+    from oracle import ddim as o_ddim, guidance as o_guid, prototypes as o_proto
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    unet, vae, guide = build_models(tiny)
+    proc = __import__("distdiff_b200.nets", fromlist=["VaeImageProcessor"]).VaeImageProcessor()
+    feats, labels = synthetic_guide_features(600 if tiny else 3000, 512 if tiny else 2048)
+    t0 = time.time()
+    fn = o_proto.l2_normalize_rows(feats.numpy())
+    gl, lc, _ = o_proto.extract_prototype_from_features(fn, labels.tolist(), a.K)
+    t_proto = time.time() - t0
+    gp, lp = (torch.from_numpy(v) for v in o_proto.normalize_prototypes(gl, lc))
+    sched = o_ddim.OracleDDIMScheduler(50)
+    b = synthetic_batch(1, 0, size=8 if tiny else 64)
+    prompt = torch.cat([b["uncond_inputs_ids"], b["input_ids"]])
+    lat = o_ddim.add_noise(b["image_latents"], torch.randn(b["image_latents"].shape, generator=torch.Generator().manual_seed(0)),
+                           o_ddim.alphas_cumprod()[981])
+    ts = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.time()
+            lat2, _ = o_guid.denoise_one_step(a, lat, sched, 981 - 20 * (i % 25), unet, prompt, None)
+            dt = time.time() - t0
+            if i >= warmup:
+                ts.append(dt)
+            log(f"cpu unguided step {i}: {dt:.2f}s")
+    t_u = sum(ts) / len(ts)
+    t0 = time.time()
+    torch.manual_seed(0)
+    lat3, score = o_guid.transform_guidance(a, lat, {"targets": b["targets"]}, [381, 361], sched, unet, prompt, None, vae, guide,
+                                            proc, torch.float32, None, gp, lp)
+    t_g = time.time() - t0
+    log(f"cpu transform_guidance: {t_g:.2f}s score {float(score):.4f}")
+    t0 = time.time()
+    with torch.no_grad():
+        vae.decode(lat3 / vae.config.scaling_factor)[0]
+    t_d = time.time() - t0
+    t_img = 50 * t_u + t_g + t_d
+    return {"value": 1.0 / t_img, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"B=1, {steps} unguided DDIM steps (mean {t_u:.2f} s) + 1 transform_guidance call ({t_g:.2f} s) + 1 VAE decode "
+                      f"({t_d:.2f} s) at full SD-v1.x/ResNet-50 size, fp32, torch CPU {cores} threads; per image = 50*t_u + t_g + t_dec "
+                      f"= {t_img:.1f} s; prototype construction (sklearn agglomerative, 3000x2048) {t_proto:.2f} s not included",
+            "t_unguided_s": t_u, "t_guided_s": t_g, "t_decode_s": t_d, "t_prototypes_s": t_proto}
+
+
+def run_reference(opt):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return 0
+    a = canonical_args(1)
+    t_wall = time.time()
+    res = cpu_reference_sample(a, opt.tiny, max(1, opt.steps), max(0, opt.warmup), log=lambda m: print(m, file=sys.stderr, flush=True))
+    line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": opt.gpus, "steps": opt.steps,
+            "warmup": opt.warmup, "ms_per_step": 1e3 / res["value"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(a, 1, 1, False, "fp32"),
+            "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": round(time.time() - t_wall, 1),
+            "note": "reference has no CPU path and cannot be imported here (diffusers/timm absent): this is the oracle port of its algorithm"}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------- ours
+def run_ours(opt):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (impl ours) needs a CUDA device; there is no CPU fallback for the hot path")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from distdiff_b200 import expand, microbench, nets, ops, prototypes
+    from distdiff_b200.scheduler import DDIMScheduler
+
+    a = canonical_args(opt.batch)
+    wd = {"fp16": torch.float16, "bf16": torch.bfloat16, "fp32": torch.float32}[opt.dtype]
+    unet, vae, guide = build_models(opt.tiny)
+    unet.to(dev, wd); vae.to(dev, wd); guide.to(dev)
+
+    # prototypes through K1/K2/K3' (sharded over ranks + NCCL all-reduce when world > 1); outside the timed region
+    feats, labels = synthetic_guide_features(600 if opt.tiny else 3000, 512 if opt.tiny else 2048)
+    coll = prototypes.NcclCollective() if world > 1 else None
+    per = -(-feats.shape[0] // world)
+    sl = slice(per * rank, min(per * (rank + 1), feats.shape[0]))
+    torch.cuda.synchronize()
+    t0 = time.time()
+    gmean, lmean = prototypes.build_prototypes(feats[sl].to(dev), labels[sl].to(dev), 100, a.K, a.cluster_method, coll=coll)
+    torch.cuda.synchronize()
+    t_proto = time.time() - t0
+    gproto, lproto = ops.normalize_rows(gmean), ops.normalize_rows(lmean)
+    guide.to(wd)
+
+    ex = expand.Expander(a, unet, vae, guide, nets.VaeImageProcessor(), DDIMScheduler(), gproto, lproto, weight_dtype=wd, device=dev,
+                         use_cuda_graph=not opt.no_cuda_graph)
+    size = 8 if opt.tiny else 64
+    host = synthetic_batch(opt.batch, rank, size=size)
+    for k in ("image_latents", "input_ids", "uncond_inputs_ids"):
+        host[k] = host[k].pin_memory()
+    resident = dict(host)
+    for k in ("image_latents", "input_ids", "uncond_inputs_ids"):
+        resident[k] = host[k].to(dev, wd)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    expand.set_seed(a.seed)
+    for i in range(max(opt.warmup, 1)):
+        img, lat, info = ex.expand_batch(resident)
+    torch.cuda.synchronize()
+    finite = bool(torch.isfinite(img.float()).all()) and bool(torch.isfinite(torch.stack(info["scores"])).all())
+    if not finite:
+        raise RuntimeError(f"non-finite output in {opt.dtype}: images finite={bool(torch.isfinite(img.float()).all())}, scores={info['scores']}")
+
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",")
+    smi_index = int(vis[local]) if len(vis) > local and vis[local].strip().isdigit() else local
+    sampler = ClockSampler(smi_index)
+    if rank == 0:
+        sampler.start()
+
+    def timed(fn):
+        barrier(); torch.cuda.synchronize()
+        l0 = ops.launch_count
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(opt.steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(); barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) * 1e-3, ops.launch_count - l0
+
+    # (1) inputs resident in HBM
+    t_res, launches = timed(lambda: ex.expand_batch(resident))
+    # (2) end to end through the public API with HOST buffers: H2D of the batch from pinned memory, D2H of the images
+    out_host = torch.empty((opt.batch, 3, size * 8, size * 8), dtype=wd).pin_memory()
+
+    def e2e_step():
+        img, _lat, info = ex.expand_batch(host)
+        out_host.copy_(img, non_blocking=True)
+        float(torch.stack(info["scores"]).sum())          # the score the reference logs (D2H read, syncs)
+    t_e2e, _ = timed(e2e_step)
+    clocks = sampler.stop() if rank == 0 else None
+    h2d = sum(host[k].numel() * host[k].element_size() for k in ("image_latents", "input_ids", "uncond_inputs_ids"))
+    d2h = out_host.numel() * out_host.element_size() + 4 * a.guidance_period
+
+    # (3) per-kernel durations of OUR kernels: one instrumented eager step (inside CUDA-graph replays the K5 launches
+    #     cannot be bracketed by events), same workload, CUDA events on the launching stream
+    ops.profiler = []
+    ex_eager = expand.Expander(a, unet, vae, guide, nets.VaeImageProcessor(), DDIMScheduler(), gproto, lproto, weight_dtype=wd,
+                               device=dev, use_cuda_graph=False)
+    ex_eager.expand_batch(resident)
+    torch.cuda.synchronize()
+    prof, ops.profiler = ops.profiler, None
+    per_kernel = {}
+    for name, nbytes, s0, s1 in prof:
+        d = per_kernel.setdefault(name, {"launches": 0, "ms": 0.0, "bytes": 0})
+        d["launches"] += 1; d["ms"] += s0.elapsed_time(s1); d["bytes"] += nbytes
+    peak, peak_src = microbench.hbm_peak_gbs()
+    dom = max(per_kernel, key=lambda k: per_kernel[k]["ms"])
+    dk = per_kernel[dom]
+    achieved = dk["bytes"] / (dk["ms"] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 5),
+                "traffic": None, "peak_source": peak_src, "launches_per_step": dk["launches"],
+                "avg_launch_us": round(1e3 * dk["ms"] / dk["launches"], 2), "algorithmic_bytes_per_launch": dk["bytes"] // dk["launches"],
+                "regime": f"launch-latency-bound: at B={opt.batch} the kernel moves {dk['bytes'] // dk['launches'] // 1024} KB per launch "
+                          "(HBM-bound sizes are in roofline_batched)",
+                "measured": "CUDA events around each launch on the launching stream, one instrumented eager step after the timed region"}
+    kernels_in_step = {k: {"launches": v["launches"], "avg_us": round(1e3 * v["ms"] / v["launches"], 2),
+                           "GBps": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1)} for k, v in per_kernel.items()}
+
+    line = None
+    if rank == 0:
+        value = world * opt.batch * opt.steps / t_res
+        e2e = world * opt.batch * opt.steps / t_e2e
+        line = {"metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": world, "steps": opt.steps, "warmup": opt.warmup,
+                "ms_per_step": round(1e3 * t_res / opt.steps, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32 arithmetic in the guidance kernels; " + opt.dtype + " latent/UNet/VAE storage (reference: fp16)",
+                "data": "synthetic", "config": workload_config(a, opt.batch, world, not opt.no_cuda_graph, opt.dtype),
+                "e2e": {"value": round(e2e, 4), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": round(1e3 * t_e2e / opt.steps, 2)},
+                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels_in_step": kernels_in_step,
+                "prototype_construction_s": round(t_proto, 4), "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1),
+                "tiny": bool(opt.tiny)}
+        if world == 1 and not opt.no_kernels:
+            recs = microbench.run(iters=5, ks=(3, 5, 10), latent_dtypes=(torch.float32, torch.float16),
+                                  want=lambda n: not n.startswith("agglo"))
+            keep = [r for r in recs if any(s in r["kernel"] for s in ("B4096", "B65536", "K1_", "K3_"))]
+            line["roofline_batched"] = [{"kernel": r["kernel"], "achieved": r["GBps"], "peak": peak, "unit": "GB/s", "frac": r["frac"],
+                                         "ms": r["ms"]} for r in keep]
+    barrier()
+    if rank == 0:
+        if world == 1 and not opt.no_cpu_baseline:
+            del ex, ex_eager
+            torch.cuda.empty_cache()
+            line["cpu_baseline"] = {k: v for k, v in cpu_reference_sample(canonical_args(1), opt.tiny, 2, 1).items()
+                                    if k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    o = parse()
+    sys.exit(run_reference(o) if o.impl == "reference" else run_ours(o))

@@ -54,6 +54,7 @@ class _GraphedStep:
         self.static_lat.copy_(latents)
         self.static_prompt.copy_(prompt_embeds)
         self.graph.replay()
+        ops.launch_count += 1  # the K5 launch inside the replayed graph
         return self.out_prev.clone(), self.out_x0
 
 

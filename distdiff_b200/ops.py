@@ -24,6 +24,27 @@ def _count(n: int = 1) -> None:
     launch_count += n
 
 
+# optional per-launch timing: set to a list to collect (entry point, algorithmic bytes, start event, end event)
+# for every call issued outside CUDA-graph capture (bench.py's roofline leg); None = no events, no overhead
+profiler = None
+
+
+def _call(name: str, algo_bytes: int, n_kernels: int, *args) -> None:
+    """Invoke one C-ABI entry point on the current stream, raise on a non-zero return."""
+    fn = getattr(_lib.lib(), name)
+    if profiler is not None and not torch.cuda.is_current_stream_capturing():
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        profiler.append((name, int(algo_bytes), e0, e1))
+    else:
+        rc = fn(*args)
+    check(rc, name)
+    _count(n_kernels)
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -76,10 +97,9 @@ def cfg_ddim_step(noise_pred: torch.Tensor, x: torch.Tensor, guidance_scale: flo
         grad = _req(grad, "grad", x.dtype)
     x_prev = torch.empty_like(x) if want_prev else None
     x0 = torch.empty_like(x) if want_x0 else None
-    check(_lib.lib().dd_cfg_ddim_fwd(pu, pt, _ptr(x), x.numel(), _code(x), float(guidance_scale), float(a_t),
-                                     float(a_prev), _ptr(grad), float(rho), _ptr(x_prev), _ptr(x0), _stream()),
-          "dd_cfg_ddim_fwd")
-    _count()
+    _call("dd_cfg_ddim_fwd", x.numel() * x.element_size() * (2 + int(pt is not None) + int(grad is not None) + int(want_prev) + int(want_x0)), 1,
+          pu, pt, _ptr(x), x.numel(), _code(x), float(guidance_scale), float(a_t),
+                                     float(a_prev), _ptr(grad), float(rho), _ptr(x_prev), _ptr(x0), _stream())
     del keep
     return x_prev, x0
 
@@ -111,9 +131,9 @@ class CfgDdimStep(torch.autograd.Function):
         if g_np is not None:
             pu = C.c_void_p(g_np.data_ptr())
             pt = C.c_void_p(g_np.data_ptr() + n * g_np.element_size()) if cfg else None
-        check(_lib.lib().dd_cfg_ddim_bwd(_ptr(g_prev), _ptr(g_x0), n, _DTYPES[dtype], s, a_t, a_prev, int(cfg), pu, pt,
-                                         _ptr(g_x), _stream()), "dd_cfg_ddim_bwd")
-        _count()
+        _call("dd_cfg_ddim_bwd", n * ref.element_size() * (int(g_prev is not None) + int(g_x0 is not None) + (2 if cfg else 1) * int(g_np is not None) + int(g_x is not None)), 1,
+              _ptr(g_prev), _ptr(g_x0), n, _DTYPES[dtype], s, a_t, a_prev, int(cfg), pu, pt,
+                                         _ptr(g_x), _stream())
         return g_np, g_x, None, None, None, None
 
 
@@ -138,9 +158,9 @@ def affine_project(x: torch.Tensor, a: torch.Tensor, b: torch.Tensor, radius: fl
         if center.shape != x.shape:
             raise DistDiffError("center must have the shape of the latents")
     y = torch.empty_like(x)
-    check(_lib.lib().dd_affine_project_fwd(_ptr(x), _ptr(a32), _ptr(b32), _ptr(center), BC, HW, _code(x), float(radius),
-                                           _ptr(y), _stream()), "dd_affine_project_fwd")
-    _count()
+    _call("dd_affine_project_fwd", x.numel() * x.element_size() * (2 + int(center is not None and radius >= 0)), 1,
+          _ptr(x), _ptr(a32), _ptr(b32), _ptr(center), BC, HW, _code(x), float(radius),
+                                           _ptr(y), _stream())
     return y
 
 
@@ -165,9 +185,9 @@ class ChannelAffine(torch.autograd.Function):
         g_a = torch.empty(BC, dtype=torch.float32, device=x.device)
         g_b = torch.empty(BC, dtype=torch.float32, device=x.device)
         g_x = torch.empty_like(x) if ctx.needs_input_grad[0] else None
-        check(_lib.lib().dd_affine_bwd(_ptr(g_y), _ptr(x), _ptr(a32), BC, HW, _code(x), _ptr(g_a), _ptr(g_b), _ptr(g_x),
-                                       _stream()), "dd_affine_bwd")
-        _count()
+        _call("dd_affine_bwd", x.numel() * x.element_size() * (2 + int(g_x is not None)), 1,
+              _ptr(g_y), _ptr(x), _ptr(a32), BC, HW, _code(x), _ptr(g_a), _ptr(g_b), _ptr(g_x),
+                                       _stream())
         ash, adt, bsh, bdt = ctx.pshape
         return g_x, g_a.reshape(ash).to(adt), g_b.reshape(bsh).to(bdt)
 
@@ -182,9 +202,8 @@ def add_noise(x: torch.Tensor, noise: torch.Tensor, a_t: float) -> torch.Tensor:
     if noise.shape != x.shape:
         raise DistDiffError("noise must have the shape of the samples")
     out = torch.empty_like(x)
-    check(_lib.lib().dd_add_noise(_ptr(x), _ptr(noise), x.numel(), _code(x), float(a_t), _ptr(out), _stream()),
-          "dd_add_noise")
-    _count()
+    _call("dd_add_noise", 3 * x.numel() * x.element_size(), 1,
+          _ptr(x), _ptr(noise), x.numel(), _code(x), float(a_t), _ptr(out), _stream())
     return out
 
 
@@ -242,10 +261,10 @@ def energy_fwd_bwd(f: torch.Tensor, targets, g: Optional[torch.Tensor], l: Optio
     per = torch.empty(B, 2, dtype=torch.float32, device=f.device)
     kstar = torch.empty(B, dtype=torch.int32, device=f.device)
     grad = torch.empty_like(f)
-    check(_lib.lib().dd_energy_fwd_bwd(_ptr(f), _ptr(y), _ptr(g), _ptr(l), B, D, Cn, K, float(gs), float(ls),
+    _call("dd_energy_fwd_bwd", B * D * 4 * (2 + int(g is not None) + (K if l is not None else 0)), 1,
+          _ptr(f), _ptr(y), _ptr(g), _ptr(l), B, D, Cn, K, float(gs), float(ls),
                                        int(bool(normalize_f)), _ptr(score), _ptr(per), _ptr(kstar), _ptr(grad),
-                                       _ptr(_ticket(f.device)), _stream()), "dd_energy_fwd_bwd")
-    _count()
+                                       _ptr(_ticket(f.device)), _stream())
     return score.reshape(()), per, kstar, grad
 
 
@@ -297,9 +316,9 @@ def rownorm_classsum(feat: torch.Tensor, perm: Optional[torch.Tensor], class_off
     out = torch.empty_like(feat)
     csum = torch.empty(C_, D, dtype=torch.float64, device=feat.device)
     ccnt = torch.empty(C_, dtype=torch.int64, device=feat.device)
-    check(_lib.lib().dd_rownorm_classsum(_ptr(feat), _ptr(perm), _ptr(class_off), N, D, C_, _ptr(out), _ptr(csum),
-                                         _ptr(ccnt), _ptr(ws), ws.numel(), _stream()), "dd_rownorm_classsum")
-    _count(2)
+    _call("dd_rownorm_classsum", 2 * N * D * 4 + N * 8, 2,
+          _ptr(feat), _ptr(perm), _ptr(class_off), N, D, C_, _ptr(out), _ptr(csum),
+                                         _ptr(ccnt), _ptr(ws), ws.numel(), _stream())
     return out, csum, ccnt
 
 
@@ -311,8 +330,8 @@ def class_mean(sum_: torch.Tensor, cnt: torch.Tensor, want_unit: bool = True):
     R = sum_.numel() // D
     mean = torch.empty(sum_.shape, dtype=torch.float32, device=sum_.device)
     unit = torch.empty_like(mean) if want_unit else None
-    check(_lib.lib().dd_class_mean(_ptr(sum_), _ptr(cnt), R, D, _ptr(mean), _ptr(unit), _stream()), "dd_class_mean")
-    _count()
+    _call("dd_class_mean", sum_.numel() * 8 + mean.numel() * 4 * (2 if want_unit else 1), 1,
+          _ptr(sum_), _ptr(cnt), R, D, _ptr(mean), _ptr(unit), _stream())
     return mean, unit
 
 
@@ -321,8 +340,8 @@ def normalize_rows(t: torch.Tensor) -> torch.Tensor:
     t = _req(t, "prototypes", torch.float32)
     D = t.shape[-1]
     out = torch.empty_like(t)
-    check(_lib.lib().dd_normalize_rows(_ptr(t), t.numel() // D, D, _ptr(out), _stream()), "dd_normalize_rows")
-    _count()
+    _call("dd_normalize_rows", 2 * t.numel() * 4, 1,
+          _ptr(t), t.numel() // D, D, _ptr(out), _stream())
     return out
 
 
@@ -333,16 +352,16 @@ def kmeans_seed(x_sorted: torch.Tensor, row_idx: torch.Tensor):
     R = row_idx.numel()
     s = torch.empty(*row_idx.shape, D, dtype=torch.float64, device=x_sorted.device)
     c = torch.empty(row_idx.shape, dtype=torch.int64, device=x_sorted.device)
-    check(_lib.lib().dd_kmeans_seed(_ptr(x_sorted), _ptr(row_idx), R, D, _ptr(s), _ptr(c), _stream()), "dd_kmeans_seed")
-    _count()
+    _call("dd_kmeans_seed", R * D * 12, 1,
+          _ptr(x_sorted), _ptr(row_idx), R, D, _ptr(s), _ptr(c), _stream())
     return s, c
 
 
 def kmeans_update(sum_: torch.Tensor, cnt: torch.Tensor, centroid: torch.Tensor, cnorm: torch.Tensor) -> None:
     Cn, K, D = centroid.shape
-    check(_lib.lib().dd_kmeans_update(_ptr(_req(sum_, "sum", torch.float64)), _ptr(_req(cnt, "cnt", torch.int64)), Cn, K, D,
-                                      _ptr(centroid), _ptr(cnorm), _stream()), "dd_kmeans_update")
-    _count()
+    _call("dd_kmeans_update", centroid.numel() * 12, 1,
+          _ptr(_req(sum_, "sum", torch.float64)), _ptr(_req(cnt, "cnt", torch.int64)), Cn, K, D,
+                                      _ptr(centroid), _ptr(cnorm), _stream())
 
 
 class KMeansBuffers:
@@ -363,10 +382,10 @@ def kmeans_assign_accum(x_sorted: torch.Tensor, class_off: torch.Tensor, buf: KM
     x_sorted = _req(x_sorted, "x_sorted", torch.float32)
     N, D = x_sorted.shape
     Cn, K, _ = buf.centroid.shape
-    check(_lib.lib().dd_kmeans_assign_accum(_ptr(x_sorted), _ptr(class_off), N, D, Cn, K, _ptr(buf.centroid), _ptr(buf.cnorm),
+    _call("dd_kmeans_assign_accum", N * D * 4 + 2 * N * 4, 2,
+          _ptr(x_sorted), _ptr(class_off), N, D, Cn, K, _ptr(buf.centroid), _ptr(buf.cnorm),
                                             _ptr(buf.assign), _ptr(buf.sum), _ptr(buf.cnt), _ptr(buf.inertia), _ptr(buf.ws),
-                                            buf.ws.numel(), _stream()), "dd_kmeans_assign_accum")
-    _count(2)
+                                            buf.ws.numel(), _stream())
 
 
 def agglo_average(x_sorted: torch.Tensor, class_off: torch.Tensor, K: int, max_class_size: int):
@@ -381,9 +400,9 @@ def agglo_average(x_sorted: torch.Tensor, class_off: torch.Tensor, K: int, max_c
     s = torch.empty(Cn, K, D, dtype=torch.float64, device=x_sorted.device)
     c = torch.empty(Cn, K, dtype=torch.int64, device=x_sorted.device)
     status = torch.empty(Cn, dtype=torch.int32, device=x_sorted.device)
-    check(_lib.lib().dd_agglo_average(_ptr(x_sorted), _ptr(class_off), Cn, D, K, max(int(max_class_size), 1), _ptr(labels),
-                                      _ptr(s), _ptr(c), _ptr(status), _ptr(ws), nbytes, _stream()), "dd_agglo_average")
-    _count()
+    _call("dd_agglo_average", N * D * 4, 1,
+          _ptr(x_sorted), _ptr(class_off), Cn, D, K, max(int(max_class_size), 1), _ptr(labels),
+                                      _ptr(s), _ptr(c), _ptr(status), _ptr(ws), nbytes, _stream())
     return labels, s, c, status
 
 

@@ -41,24 +41,18 @@ class Collective:
         return t
 
 
-class NcclCollective(Collective):
-    """NCCL through the C ABI (dd_comm_*) for the per-iteration all-reduce; torch.distributed (same NCCL) for
-    the one-off ragged all-gather.  Requires torch.distributed to be initialised (torchrun)."""
+class TorchDistCollective(Collective):
+    """torch.distributed plumbing (NCCL on the GPUs; gloo in the CPU tests of the sharding logic)."""
 
     def __init__(self):
         import torch.distributed as dist
         self.dist = dist
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
 
-        def exchange(uid: bytes) -> bytes:
-            box = [uid]
-            dist.broadcast_object_list(box, src=0)
-            return box[0]
-
-        self.comm = ops.Comm(self.rank, self.world, exchange)
-
     def allreduce(self, sum_, cnt):
-        self.comm.allreduce(sum_, cnt)
+        for t in (sum_, cnt):
+            if t is not None:
+                self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
 
     def allgather_rows(self, t):
         n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
@@ -71,6 +65,26 @@ class NcclCollective(Collective):
         out = [torch.empty_like(pad) for _ in range(self.world)]
         self.dist.all_gather(out, pad)
         return torch.cat([o[:s] for o, s in zip(out, sizes)], 0)
+
+
+class NcclCollective(TorchDistCollective):
+    """The per-iteration all-reduce of centroid / class sums + counts goes through the C ABI (dd_comm_allreduce:
+    one ncclGroup on the caller's stream, straight on the buffers the reduce kernel wrote); the one-off ragged
+    all-gather stays on torch.distributed (same NCCL).  Requires torch.distributed to be initialised (torchrun)."""
+
+    def __init__(self):
+        super().__init__()
+        dist = self.dist
+
+        def exchange(uid: bytes) -> bytes:
+            box = [uid]
+            dist.broadcast_object_list(box, src=0)
+            return box[0]
+
+        self.comm = ops.Comm(self.rank, self.world, exchange)
+
+    def allreduce(self, sum_, cnt):
+        self.comm.allreduce(sum_, cnt)
 
 
 def _class_shard(counts: np.ndarray, world: int):

@@ -269,22 +269,25 @@ def run_ours(opt):
     if rank == 0:
         sampler.start()
 
-    def timed(fn):
+    def timed(fn, tag):
         barrier(); torch.cuda.synchronize()
+        torch.cuda.nvtx.range_push(tag)      # ncu --nvtx --nvtx-include "<tag>/" profiles exactly the timed region
         l0 = ops.launch_count
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(opt.steps):
             fn()
         e1.record()
-        torch.cuda.synchronize(); barrier()
+        torch.cuda.synchronize()
+        torch.cuda.nvtx.range_pop()
+        barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms) * 1e-3, ops.launch_count - l0
 
     # (1) inputs resident in HBM
-    t_res, launches = timed(lambda: ex.expand_batch(resident))
+    t_res, launches = timed(lambda: ex.expand_batch(resident), "dd_timed_resident")
     # (2) end to end through the public API with HOST buffers: H2D of the batch from pinned memory, D2H of the images
     out_host = torch.empty((opt.batch, 3, size * 8, size * 8), dtype=wd).pin_memory()
 
@@ -292,7 +295,7 @@ def run_ours(opt):
         img, _lat, info = ex.expand_batch(host)
         out_host.copy_(img, non_blocking=True)
         float(torch.stack(info["scores"]).sum())          # the score the reference logs (D2H read, syncs)
-    t_e2e, _ = timed(e2e_step)
+    t_e2e, _ = timed(e2e_step, "dd_timed_e2e")
     clocks = sampler.stop() if rank == 0 else None
     h2d = sum(host[k].numel() * host[k].element_size() for k in ("image_latents", "input_ids", "uncond_inputs_ids"))
     d2h = out_host.numel() * out_host.element_size() + 4 * a.guidance_period

@@ -88,15 +88,19 @@ __device__ __forceinline__ void store_f64x4(double* dst, double a, double b, dou
 // ---------------------------------------------------------------------------------------------------
 // K3: assign + accumulate
 // ---------------------------------------------------------------------------------------------------
-template <int K, int R, typename AccT>
+// INERTIA adds ||x||^2 as a (K+1)-th reduced value per row (needed only to report sum ||x - mu*||^2); without it
+// more rows fit one reduction round (R*KV <= 32), which amortises the per-batch barrier and argmin tail.
+template <int K, int R, bool INERTIA>
 __global__ void __launch_bounds__(PK_THREADS, 1)
 kmeans_stream_kernel(const float* __restrict__ x, const int64_t* __restrict__ class_off, int64_t N, int D, int C,
                      const float* __restrict__ centroid, const float* __restrict__ cnorm, int32_t* __restrict__ assign,
                      double* __restrict__ ws_sum, int64_t* __restrict__ ws_cnt, double* __restrict__ ws_inertia,
                      int stages) {
-    constexpr int V = R * (K + 1);      // per row: K dots + ||x||^2
+    constexpr int KV = K + (INERTIA ? 1 : 0);  // reduced values per row: K dots (+ ||x||^2)
+    constexpr int V = R * KV;
     constexpr int P = pow2_ge(V);
-    static_assert(V <= 32, "R*(K+1) must fit one warp");
+    static_assert(V <= 32, "R*KV must fit one warp");
+    using AccT = float;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const size_t stage_elems = (size_t)R * D;
     float* ring = reinterpret_cast<float*>(smem_raw);
@@ -193,12 +197,14 @@ kmeans_stream_kernel(const float* __restrict__ x, const int64_t* __restrict__ cl
                 float2 a = make_float2(0.f, 0.f);
 #pragma unroll
                 for (int ch = 0; ch < PK_CH; ++ch) a = dot4(xv[r][ch], mu[k][ch], a);
-                v[r * (K + 1) + k] = a.x + a.y;
+                v[r * KV + k] = a.x + a.y;
             }
-            float2 a = make_float2(0.f, 0.f);
+            if constexpr (INERTIA) {
+                float2 a = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int ch = 0; ch < PK_CH; ++ch) a = dot4(xv[r][ch], xv[r][ch], a);
-            v[r * (K + 1) + K] = a.x + a.y;
+                for (int ch = 0; ch < PK_CH; ++ch) a = dot4(xv[r][ch], xv[r][ch], a);
+                v[r * KV + K] = a.x + a.y;
+            }
         }
         xreduce<P, 16>(v, lane);
         if ((lane & (32 / P - 1)) == 0) red[(buf * PK_WARPS + warp) * 32 + (lane >> (5 - log2i(P)))] = v[0];
@@ -217,24 +223,26 @@ kmeans_stream_kernel(const float* __restrict__ x, const int64_t* __restrict__ cl
             for (int w = 0; w < PK_WARPS; ++w) tot += red[(buf * PK_WARPS + w) * 32 + lane];  // fixed order
         }
         // lane r < R: argmin_k (cnorm_k - 2 <x_r, mu_k>), lowest k on ties
-        float best = INFINITY, xn = 0.f;
+        float best = INFINITY;
         int bestk = 0;
-        const int rbase = (lane < R ? lane : 0) * (K + 1);
+        const int rbase = (lane < R ? lane : 0) * KV;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const float d = __shfl_sync(0xffffffffu, tot, rbase + k);
             const float sc = fmaf(-2.f, d, cn[k]);
             if (sc < best) { best = sc; bestk = k; }
         }
-        xn = __shfl_sync(0xffffffffu, tot, rbase + K);
-        const float d2 = fmaxf(xn + best, 0.f);
+        float d2 = 0.f;
+        if constexpr (INERTIA) d2 = fmaxf(__shfl_sync(0xffffffffu, tot, rbase + K) + best, 0.f);
         if (warp == 0 && lane < bn) assign[brow + lane] = bestk;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int kr = __shfl_sync(0xffffffffu, bestk, r);
-            const float dr = __shfl_sync(0xffffffffu, d2, r);
+            if constexpr (INERTIA) {
+                const float dr = __shfl_sync(0xffffffffu, d2, r);
+                if (r < bn) inert += (double)dr;
+            }
             if (r < bn) {
-                inert += (double)dr;
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
                     if (kr == k) {  // CTA-uniform
@@ -531,14 +539,14 @@ static size_t smem_bytes(int stages, int R, int D) {
     return (size_t)stages * R * D * sizeof(float) + PK_MAX_STAGES * sizeof(uint64_t) + 2 * PK_WARPS * 32 * sizeof(float);
 }
 
-template <int K, int R, typename AccT>
+template <int K, int R, bool INERTIA>
 static int launch_kmeans(const float* x, const int64_t* class_off, int64_t N, int D, int C, const float* centroid,
                          const float* cnorm, int32_t* assign, double* ws_sum, int64_t* ws_cnt, double* ws_inertia, int G,
                          cudaStream_t st) {
     const int stages = pick_stages(R, D);
     DD_REQUIRE(stages >= 2, DD_EUNSUPPORTED, "kmeans: D=%d too large for the shared-memory ring", D);
     const size_t smem = smem_bytes(stages, R, D);
-    auto kern = kmeans_stream_kernel<K, R, AccT>;
+    auto kern = kmeans_stream_kernel<K, R, INERTIA>;
     DD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<G, PK_THREADS, smem, st>>>(x, class_off, N, D, C, centroid, cnorm, assign, ws_sum, ws_cnt, ws_inertia, stages);
     DD_LAUNCH_OK();
@@ -640,13 +648,16 @@ int dd_kmeans_assign_accum(const float* x_sorted, const int64_t* class_off, int6
     double* ws_in = (double*)((char*)ws + w.inertia_off);
     int rc = 0;
     if (N > 0) {
-#define DD_KM(KK, RR, ACC) \
-    case KK: rc = dd::launch_kmeans<KK, RR, ACC>(x_sorted, class_off, N, D, C, centroid, cnorm, assign, ws_sum, ws_cnt, ws_in, G, st); break;
+#define DD_KM(KK, RI, RF)                                                                                                   \
+    case KK:                                                                                                                \
+        rc = inertia ? dd::launch_kmeans<KK, RI, true>(x_sorted, class_off, N, D, C, centroid, cnorm, assign, ws_sum, ws_cnt, ws_in, G, st) \
+                     : dd::launch_kmeans<KK, RF, false>(x_sorted, class_off, N, D, C, centroid, cnorm, assign, ws_sum, ws_cnt, ws_in, G, st); \
+        break;
+        // rows per batch: with inertia R*(K+1) <= 32, without R*K <= 32 (capped by registers / ring stage size)
         switch (K) {
-            DD_KM(1, 8, float) DD_KM(2, 8, float) DD_KM(3, 8, float)
-            DD_KM(4, 4, float) DD_KM(5, 4, float) DD_KM(6, 4, float) DD_KM(7, 4, float)
-            DD_KM(8, 2, float) DD_KM(9, 2, float) DD_KM(10, 2, float) DD_KM(11, 2, float) DD_KM(12, 2, float)
-            DD_KM(13, 2, float) DD_KM(14, 2, float) DD_KM(15, 2, float)
+            DD_KM(1, 8, 8) DD_KM(2, 8, 8) DD_KM(3, 8, 8) DD_KM(4, 4, 8) DD_KM(5, 4, 6) DD_KM(6, 4, 5) DD_KM(7, 4, 4)
+            DD_KM(8, 2, 4) DD_KM(9, 2, 3) DD_KM(10, 2, 3) DD_KM(11, 2, 2) DD_KM(12, 2, 2)
+            DD_KM(13, 2, 2) DD_KM(14, 2, 2) DD_KM(15, 2, 2)
         }
 #undef DD_KM
         if (rc) return rc;

@@ -377,14 +377,15 @@ class KMeansBuffers:
         self.ws = proto_workspace(D, C_, K, device)
 
 
-def kmeans_assign_accum(x_sorted: torch.Tensor, class_off: torch.Tensor, buf: KMeansBuffers) -> None:
-    """K3: one assignment + accumulation pass; results land in buf.assign / buf.sum / buf.cnt / buf.inertia."""
+def kmeans_assign_accum(x_sorted: torch.Tensor, class_off: torch.Tensor, buf: KMeansBuffers, want_inertia: bool = False) -> None:
+    """K3: one assignment + accumulation pass; results land in buf.assign / buf.sum / buf.cnt (and buf.inertia when
+    ``want_inertia``: that variant reduces one more value per row, so fewer rows share a reduction round)."""
     x_sorted = _req(x_sorted, "x_sorted", torch.float32)
     N, D = x_sorted.shape
     Cn, K, _ = buf.centroid.shape
     _call("dd_kmeans_assign_accum", N * D * 4 + 2 * N * 4, 2,
           _ptr(x_sorted), _ptr(class_off), N, D, Cn, K, _ptr(buf.centroid), _ptr(buf.cnorm),
-                                            _ptr(buf.assign), _ptr(buf.sum), _ptr(buf.cnt), _ptr(buf.inertia), _ptr(buf.ws),
+                                            _ptr(buf.assign), _ptr(buf.sum), _ptr(buf.cnt), _ptr(buf.inertia) if want_inertia else None, _ptr(buf.ws),
                                             buf.ws.numel(), _stream())
 
 

@@ -174,7 +174,7 @@ def build_prototypes(features: torch.Tensor, labels: torch.Tensor, num_classes: 
         ops.kmeans_update(s, n, buf.centroid, buf.cnorm)
         inertia = []
         for _ in range(int(kmeans_iters)):
-            ops.kmeans_assign_accum(xs, off, buf)                              # K3
+            ops.kmeans_assign_accum(xs, off, buf, want_inertia=return_debug)   # K3
             coll.allreduce(buf.sum, buf.cnt)                                   # centroid sums + counts over NVLink
             ops.kmeans_update(buf.sum, buf.cnt, buf.centroid, buf.cnorm)
             if return_debug:

@@ -360,7 +360,7 @@ def test_kmeans_one_iteration_vs_oracle(ops, cuda_device, N, C, D, K):
     mu = (mu + 0.05 * rng.normal(size=mu.shape)).astype(np.float32)
     buf.centroid.copy_(torch.from_numpy(mu))
     buf.cnorm.copy_(torch.from_numpy((mu.astype(np.float64) ** 2).sum(-1).astype(np.float32)))
-    ops.kmeans_assign_accum(xs, off, buf)
+    ops.kmeans_assign_accum(xs, off, buf, want_inertia=True)
     assign = buf.assign.cpu().numpy()
     inert_ref = 0.0
     for c in range(C):
@@ -378,9 +378,14 @@ def test_kmeans_one_iteration_vs_oracle(ops, cuda_device, N, C, D, K):
         inert_ref += (((Xc.astype(np.float64) - mu[c][a].astype(np.float64)) ** 2).sum())
     assert abs(float(buf.inertia) - inert_ref) <= 1e-4 * inert_ref + 1e-6
     # reproducible bit for bit
-    s1 = buf.sum.clone(); a1 = buf.assign.clone()
-    ops.kmeans_assign_accum(xs, off, buf)
+    s1 = buf.sum.clone(); a1 = buf.assign.clone(); c1 = buf.cnt.clone()
+    ops.kmeans_assign_accum(xs, off, buf, want_inertia=True)
     assert torch.equal(s1, buf.sum) and torch.equal(a1, buf.assign)
+    # the inertia-free variant (more rows per reduction round) gives the same assignment / counts, sums to fp32 rounding
+    ops.kmeans_assign_accum(xs, off, buf, want_inertia=False)
+    assert torch.equal(a1, buf.assign) and torch.equal(c1, buf.cnt)
+    assert float((s1 - buf.sum).abs().max()) <= 2e-6 * float(s1.abs().max())
+    s1 = buf.sum.clone()
     # update kernel
     old = buf.centroid.clone()
     ops.kmeans_update(buf.sum, buf.cnt, buf.centroid, buf.cnorm)
@@ -402,8 +407,10 @@ def test_kmeans_tiny_and_empty(ops, cuda_device):
     buf.centroid.copy_(torch.randn(4, 2, 64)); buf.cnorm.copy_((buf.centroid.double() ** 2).sum(-1).float())
     ops.kmeans_assign_accum(xs, off, buf)
     assert buf.cnt.sum(-1).cpu().tolist() == [3, 0, 4, 2]
+    ops.kmeans_assign_accum(xs, off, buf, want_inertia=True)
+    assert buf.cnt.sum(-1).cpu().tolist() == [3, 0, 4, 2]
     xs0 = torch.empty(0, 64, device=cuda_device)
     off0 = torch.zeros(5, dtype=torch.int64, device=cuda_device)
     buf0 = ops.KMeansBuffers(0, 64, 4, 2, cuda_device)
-    ops.kmeans_assign_accum(xs0, off0, buf0)
+    ops.kmeans_assign_accum(xs0, off0, buf0, want_inertia=True)
     assert int(buf0.cnt.sum()) == 0 and float(buf0.inertia) == 0.0

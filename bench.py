@@ -39,6 +39,7 @@ def parse():
     p.add_argument("--batch", type=int, default=4, help="images per step and GPU (train_batch_size)")
     p.add_argument("--dtype", default="fp16", choices=["fp16", "bf16", "fp32"], help="UNet/VAE/latent storage type (reference: fp16)")
     p.add_argument("--no-cuda-graph", action="store_true")
+    p.add_argument("--no-channels-last", action="store_true", help="keep UNet/VAE/guide in NCHW (PyTorch-side layout choice)")
     p.add_argument("--no-kernels", action="store_true", help="skip the batched kernel micro-benchmarks")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--tiny", action="store_true", help="tiny networks (CI smoke of bench.py itself; not a valid number)")
@@ -53,12 +54,13 @@ def canonical_args(batch):
                                  num_classes=100, arch="resnet50", dataset="caltech-101")
 
 
-def workload_config(a, batch, world, graph, dtype):
+def workload_config(a, batch, world, graph, dtype, cl=False):
     return {"workload": "Caltech-101 5x expansion, ResNet-50 guide, SD v1.4 512px, 50 DDIM steps (BASELINE configs[1])",
             "images_per_step_per_gpu": batch, "ddim_steps": 50, "guidance": "transform_guidance t=381 period 2",
             "K": a.K, "cluster_method": a.cluster_method, "cfg_scale": a.guidance_scale, "latent": "4x64x64",
             "storage_dtype": dtype, "weights": "random-init SD-v1.x UNet (859.5M) / VAE / ResNet-50",
             "parallelism": f"image-split x{world} (no collective)", "cuda_graph_unguided_step": bool(graph),
+            "channels_last": bool(cl),
             "l2": "every step streams ~3.4 GB of UNet weights+activations (> 126 MB L2) between two launches of the same kernel; "
                   "micro-benchmarks evict L2 by reading 512 MB before each timed launch"}
 
@@ -227,6 +229,9 @@ def run_ours(opt):
     wd = {"fp16": torch.float16, "bf16": torch.bfloat16, "fp32": torch.float32}[opt.dtype]
     unet, vae, guide = build_models(opt.tiny)
     unet.to(dev, wd); vae.to(dev, wd); guide.to(dev)
+    if not opt.no_channels_last:   # PyTorch-side: NHWC weights let cuDNN skip its per-conv nchw<->nhwc transposes (14 % of a step)
+        for m in (unet, vae, guide):
+            m.to(memory_format=torch.channels_last)
 
     # prototypes through K1/K2/K3' (sharded over ranks + NCCL all-reduce when world > 1); outside the timed region
     feats, labels = synthetic_guide_features(600 if opt.tiny else 3000, 512 if opt.tiny else 2048)
@@ -332,7 +337,7 @@ def run_ours(opt):
         line = {"metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": world, "steps": opt.steps, "warmup": opt.warmup,
                 "ms_per_step": round(1e3 * t_res / opt.steps, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32 arithmetic in the guidance kernels; " + opt.dtype + " latent/UNet/VAE storage (reference: fp16)",
-                "data": "synthetic", "config": workload_config(a, opt.batch, world, not opt.no_cuda_graph, opt.dtype),
+                "data": "synthetic", "config": workload_config(a, opt.batch, world, not opt.no_cuda_graph, opt.dtype, not opt.no_channels_last),
                 "e2e": {"value": round(e2e, 4), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": round(1e3 * t_e2e / opt.steps, 2)},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels_in_step": kernels_in_step,

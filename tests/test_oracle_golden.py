@@ -64,10 +64,13 @@ def test_denoise_one_step_vs_reference(golden, name):
     with torch.no_grad():
         prev, x0 = guidance.denoise_one_step(args, case["latents"], sched, case["denoise"]["t"], unet,
                                              case["prompt_embeds"], None)
-    assert torch.equal(prev, case["denoise"]["prev"]) and torch.equal(x0, case["denoise"]["x0"])
+    # The stand-in UNet forward goes through the host's conv kernels (oneDNN picks per-ISA code, so the last
+    # bit can differ between hosts); the scheduler arithmetic on the golden noise_pred below is bit-exact.
+    assert torch.allclose(prev, case["denoise"]["prev"], rtol=0, atol=2e-6)
+    assert torch.allclose(x0, case["denoise"]["x0"], rtol=0, atol=2e-6)
     a_t, a_prev = ddim.alpha_pair(case["denoise"]["t"])
     p2, x2 = ddim.cfg_ddim_step(case["denoise"]["noise_pred"], case["latents"], args.guidance_scale, a_t, a_prev)
-    assert torch.equal(p2, prev) and torch.equal(x2, x0)
+    assert torch.equal(p2, case["denoise"]["prev"]) and torch.equal(x2, case["denoise"]["x0"])
 
 
 @pytest.mark.parametrize("name", GUIDE_CASES)
@@ -80,8 +83,10 @@ def test_transform_guidance_vs_reference(golden, name):
         lat, score = guidance.transform_guidance(args, case["latents"].clone(), {"targets": case["targets"]},
                                                  [381, 361], sched, unet, case["prompt_embeds"], None, vae, enc, proc,
                                                  torch.float32, None, gp, lp)
-        assert torch.allclose(lat, case[key]["latents_out"], rtol=0, atol=1e-6)
-        assert abs(float(score) - case[key]["score"]) < 1e-6
+        # the nets run on this host's conv/GEMM kernels (last-bit host dependence, amplified by rho): 1e-5 here,
+        # against north_star's 1e-3 bar for per-step latents
+        assert (lat - case[key]["latents_out"]).abs().max() <= 1e-5 * case[key]["latents_out"].abs().max()
+        assert abs(float(score) - case[key]["score"]) < 1e-5 * max(1.0, abs(case[key]["score"]))
 
 
 @pytest.mark.parametrize("name", GUIDE_CASES)
@@ -94,7 +99,7 @@ def test_direct_guidance_vs_reference(golden, name):
                                                   sched, unet, case["prompt_embeds"], None, vae, enc, proc,
                                                   torch.float32, None, gp, lp)
         assert torch.allclose(lat, case[key]["latents_out"], rtol=0, atol=1e-6)
-        assert torch.equal(x0, case[key]["x0"])
+        assert torch.allclose(x0, case[key]["x0"], rtol=0, atol=2e-6)   # through the host's conv kernels
         assert abs(float(score) - case[key]["score"]) < 1e-6
 
 

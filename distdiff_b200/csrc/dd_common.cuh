@@ -138,6 +138,57 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
     return *reinterpret_cast<float2*>(&rd);
 }
 
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a);
+    unsigned long long rb = *reinterpret_cast<unsigned long long*>(&b);
+    unsigned long long rd;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a);
+    unsigned long long rb = *reinterpret_cast<unsigned long long*>(&b);
+    unsigned long long rd;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    return *reinterpret_cast<float2*>(&rd);
+}
+
+// The same packed ops on opaque 64-bit register pairs.  Keeping the pair as one b64 value (built once with
+// pack2) stops the compiler from re-assembling it from two scalar registers with MOVs at every use.
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pack2(float lo, float hi) {
+    f32x2_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float2 unpack2(f32x2_t v) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+// d = a * (x, x) + c   (ptxas folds the broadcast into a scalar `R.F32` operand)
+__device__ __forceinline__ f32x2_t ffma2_bcast(f32x2_t a, float x, f32x2_t c) {
+    f32x2_t d;
+    asm("{\n.reg .b64 t;\nmov.b64 t, {%2, %2};\nfma.rn.f32x2 %0, %1, t, %3;\n}" : "=l"(d) : "l"(a), "f"(x), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2_t fmul2_bcast(f32x2_t a, float x) {
+    f32x2_t d;
+    asm("{\n.reg .b64 t;\nmov.b64 t, {%2, %2};\nmul.rn.f32x2 %0, %1, t;\n}" : "=l"(d) : "l"(a), "f"(x));
+    return d;
+}
+__device__ __forceinline__ f32x2_t fadd2_p(f32x2_t a, f32x2_t b) {
+    f32x2_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+// a + (lo, hi)
+__device__ __forceinline__ f32x2_t fadd2_s(f32x2_t a, float lo, float hi) {
+    f32x2_t d;
+    asm("{\n.reg .b64 t;\nmov.b64 t, {%2, %3};\nadd.rn.f32x2 %0, %1, t;\n}" : "=l"(d) : "l"(a), "f"(lo), "f"(hi));
+    return d;
+}
+
 // ---- mbarrier + 1-D bulk async copy (TMA engine, UBLKCP) -----------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -153,17 +204,26 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
+    return ok != 0;
+}
+// Bounded spin: a protocol bug becomes a trapped launch (reported through the C ABI's error code) instead of a
+// hung GPU.  Every legitimate wait in this library ends within microseconds; 2^24 timed-out polls never happen.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins == (1u << 24)) __trap();
+    }
 }
 // global -> shared bulk copy of `bytes` (multiple of 16, both addresses 16-byte aligned); completion is
 // signalled on `bar` through complete_tx.

@@ -283,7 +283,7 @@ kmeans_stream_kernel(const float* __restrict__ x, const int64_t* __restrict__ cl
 //   * rows are re-read from the ring for the accumulation (CTA-uniform jump on k*, 4 FADD2 per row).
 constexpr int K2_WARPS = 8;                    // compute warps
 constexpr int K2_COMPUTE = K2_WARPS * 32;
-constexpr int K2_THREADS = K2_COMPUTE;
+constexpr int K2_THREADS = 2 * K2_COMPUTE;      // 8 DOT warps + 8 ACC warps
 constexpr int K2_R = 6;                        // rows per batch
 constexpr int K2_TR = 34;                      // float2 per transposition row: 272 B keeps LDS.128 conflict-free
 constexpr int K2_MAXK = 10;
@@ -310,11 +310,15 @@ __device__ __forceinline__ void acc_add(f32x2_t (&acc)[K][4], int k, const float
 
 // FULL: D == 8 * K2_COMPUTE (2048), every thread owns both of its chunks -> no predicates on the row loads.
 //
-// The loop is skewed by one batch: an iteration first runs phase A (dots -> warp totals) of batch i+1 and only
-// then finishes batch i (cross-warp sum, argmin, accumulation).  Warps meet through an mbarrier per `cross`
-// buffer that was armed a whole phase A earlier, so nobody waits at it and the two warps of a scheduler drift
-// out of phase -- one is in the FMA-bound phase A while the other sits in the latency-bound tail.
-constexpr int K2_CROSS = 4;  // cross buffers in flight: a fast warp may write batch i+2 while a slow one still reads i-1
+// Warp-specialised: 16 warps, 128 registers each.  The two register-hungry states never live in one thread:
+//   * DOT warps 0-7 hold the centroid pairs (8*KP f32x2) and run phase A: dots of the 6 rows of a batch, the
+//     warp-private transposition sum, warp totals -> cross[buf]; arrive on cbar[buf]; release the ring stage.
+//   * ACC warps 8-15 hold the per-cluster sums (4*K f32x2): wait cbar[buf], add the 8 warp totals in fixed order,
+//     argmin, write assignments, re-read the rows from the ring and accumulate; release the stage; the first ACC
+//     lane refills it through the TMA engine once all 16 warps have released it.
+// The DOT warps run up to `stages` batches ahead, so a scheduler always has FMA-bound and latency-bound warps to
+// pick from (4 per scheduler instead of the 2 a 255-register thread allows).
+constexpr int K2_CROSS = 4;  // cross buffers; the ring is capped at K2_CROSS stages so a buffer is never overwritten early
 
 template <int K, bool FULL>
 __global__ void __launch_bounds__(K2_THREADS, 1)
@@ -336,11 +340,12 @@ kmeans_pair_kernel(const float* __restrict__ x, const int64_t* __restrict__ clas
     int* cnt_s = reinterpret_cast<int*>(cross + K2_CROSS * K2_WARPS * 32);   // [16]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int t = tid & (K2_COMPUTE - 1);   // column owner index inside the role
     const int G = gridDim.x, g = blockIdx.x;
     const int64_t r0 = N * g / G, r1 = N * (g + 1) / G;
 
     if (tid == 0) {
-        for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], K2_WARPS); }
+        for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 2 * K2_WARPS); }
         for (int i = 0; i < K2_CROSS; ++i) mbar_init(&cbar[i], K2_WARPS);
         mbar_fence_init();
     }
@@ -348,14 +353,100 @@ kmeans_pair_kernel(const float* __restrict__ x, const int64_t* __restrict__ clas
     __syncthreads();
     if (r0 >= r1) return;
 
-    // producer cursor (thread 0 only): prologue fills every stage
-    int64_t irow = r0;
-    int ic = find_class(class_off, C, r0);
-    int64_t iend = __ldg(class_off + ic + 1);
-    // batch cursor of the compute side (every thread; captured BEFORE thread 0's prologue advances the producer cursor)
+    const int nch = D >> 2;
+    const int chunk0 = t, chunk1 = t + K2_COMPUTE;
+    const bool own0 = FULL || chunk0 < nch, own1 = FULL || chunk1 < nch;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    // batch cursor (every thread walks the same deterministic batch sequence)
     int64_t crow = r0;
-    int cc = ic;
-    int64_t cend = iend;
+    int cc = find_class(class_off, C, r0);
+    int64_t cend = __ldg(class_off + cc + 1);
+    int stage = 0, buf = 0;
+    uint32_t par = 0, cpar = 0;
+    auto advance = [&]() {
+        if (++stage == stages) { stage = 0; par ^= 1; }
+        if (++buf == K2_CROSS) { buf = 0; cpar ^= 1; }
+    };
+
+    if (warp < K2_WARPS) {
+        // =========================== DOT warps ===========================
+        f32x2_t mu2[KP][8];
+        const float one = N >= 0 ? 1.0f : 2.0f;  // always 1; not a compile-time constant
+        int mu_class = -1;
+        float2* my_tr = tr + (size_t)warp * SLOTS * K2_TR;
+        const bool slot_ok = lane < SLOTS;
+        while (crow < r1) {
+            int64_t brow; int bn, bc;
+            take_batch(class_off, r1, R, crow, cc, cend, brow, bn, bc);
+            if (bc != mu_class) {
+                mu_class = bc;
+#pragma unroll
+                for (int p = 0; p < KP; ++p) {
+                    const float4* c0 = reinterpret_cast<const float4*>(centroid + ((int64_t)bc * K + 2 * p) * D);
+                    const float4* c1 = reinterpret_cast<const float4*>(centroid + ((int64_t)bc * K + 2 * p + 1) * D);
+                    const bool has1 = 2 * p + 1 < K;
+                    const float4 a0 = own0 ? __ldg(c0 + chunk0) : zero4, a1 = own1 ? __ldg(c0 + chunk1) : zero4;
+                    const float4 b0 = (has1 && own0) ? __ldg(c1 + chunk0) : zero4, b1 = (has1 && own1) ? __ldg(c1 + chunk1) : zero4;
+                    // x * 1 + (-0) == x bit for bit; `one` is opaque to ptxas, so each pair is DEFINED by an FFMA2 result
+                    // register pair and cannot be rematerialised from the two scalar loads inside the hot loop
+                    const f32x2_t nz = pack2(-0.f, -0.f);
+                    mu2[p][0] = ffma2_bcast(pack2(a0.x, b0.x), one, nz); mu2[p][1] = ffma2_bcast(pack2(a0.y, b0.y), one, nz);
+                    mu2[p][2] = ffma2_bcast(pack2(a0.z, b0.z), one, nz); mu2[p][3] = ffma2_bcast(pack2(a0.w, b0.w), one, nz);
+                    mu2[p][4] = ffma2_bcast(pack2(a1.x, b1.x), one, nz); mu2[p][5] = ffma2_bcast(pack2(a1.y, b1.y), one, nz);
+                    mu2[p][6] = ffma2_bcast(pack2(a1.z, b1.z), one, nz); mu2[p][7] = ffma2_bcast(pack2(a1.w, b1.w), one, nz);
+                }
+            }
+            mbar_wait(&full[stage], par);
+            const float* st = ring + (size_t)stage * stage_elems;
+            // phase A: packed partial dots of every row of the batch -> warp-private transposition buffer
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const float4 xa = own0 ? *reinterpret_cast<const float4*>(st + (size_t)r * D + chunk0 * 4) : zero4;
+                const float4 xb = own1 ? *reinterpret_cast<const float4*>(st + (size_t)r * D + chunk1 * 4) : zero4;
+                const float xs[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+                f32x2_t dp[KP];
+#pragma unroll
+                for (int p = 0; p < KP; ++p) dp[p] = fmul2_bcast(mu2[p][0], xs[0]);
+#pragma unroll
+                for (int j = 1; j < 8; ++j)
+#pragma unroll
+                    for (int p = 0; p < KP; ++p) dp[p] = ffma2_bcast(mu2[p][j], xs[j], dp[p]);
+#pragma unroll
+                for (int p = 0; p < KP; ++p) reinterpret_cast<f32x2_t*>(my_tr)[(r * KP + p) * K2_TR + lane] = dp[p];
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[stage]);  // the DOT side is done with the rows
+            // lane = slot: sum the 32 lanes' partials of that slot (fixed order, 8 chains)
+            {
+                const float4* row = reinterpret_cast<const float4*>(my_tr + (slot_ok ? lane : 0) * K2_TR);
+                f32x2_t c[8];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 u = row[i];
+                    c[2 * i] = pack2(u.x, u.y); c[2 * i + 1] = pack2(u.z, u.w);
+                }
+#pragma unroll
+                for (int i = 4; i < 16; ++i) {
+                    const float4 u = row[i];
+                    c[(2 * i) & 7] = fadd2_s(c[(2 * i) & 7], u.x, u.y); c[(2 * i + 1) & 7] = fadd2_s(c[(2 * i + 1) & 7], u.z, u.w);
+                }
+                const f32x2_t tot = fadd2_p(fadd2_p(fadd2_p(c[0], c[1]), fadd2_p(c[2], c[3])), fadd2_p(fadd2_p(c[4], c[5]), fadd2_p(c[6], c[7])));
+                reinterpret_cast<f32x2_t*>(cross)[(buf * K2_WARPS + warp) * 32 + lane] = tot;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&cbar[buf]);
+            advance();
+        }
+        return;
+    }
+
+    // =========================== ACC warps ===========================
+    const bool leader = tid == K2_COMPUTE;  // first ACC lane: drives the TMA engine
+    // producer cursor (leader only): prologue fills every stage
+    int64_t irow = crow;
+    int ic = cc;
+    int64_t iend = cend;
     auto refill = [&](int s) {
         int64_t br; int bn, bc;
         take_batch(class_off, r1, R, irow, ic, iend, br, bn, bc);
@@ -363,25 +454,18 @@ kmeans_pair_kernel(const float* __restrict__ x, const int64_t* __restrict__ clas
         mbar_expect_tx(&full[s], bytes);
         bulk_g2s(ring + (size_t)s * stage_elems, x + br * D, bytes, &full[s]);
     };
-    if (tid == 0)
+    if (leader)
         for (int s = 0; s < stages && irow < r1; ++s) refill(s);
 
-    const int nch = D >> 2;
-    const int chunk0 = tid, chunk1 = tid + K2_COMPUTE;
-    const bool own0 = FULL || chunk0 < nch, own1 = FULL || chunk1 < nch;
     const int my_p = lane % KP, my_row = lane / KP;
     const bool slot_ok = lane < SLOTS;
-
-    f32x2_t mu2[KP][8];
     f32x2_t acc[K][4];
 #pragma unroll
     for (int k = 0; k < K; ++k)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[k][j] = 0ull;
-    const float one = N >= 0 ? 1.0f : 2.0f;  // always 1; not a compile-time constant
-    float2 cn2_a = make_float2(INFINITY, INFINITY);  // ||mu||^2 of this lane's cluster pair, class of the phase-A batch
-    float2 cn2_f = cn2_a;                            // same for the batch being finished
-    int mu_class = -1;
+    float2 cn2 = make_float2(INFINITY, INFINITY);  // ||mu||^2 of this lane's cluster pair
+    int cur = -1;
 
     auto flush = [&](int c) {
         const int64_t slot = (int64_t)g + c;
@@ -394,147 +478,77 @@ kmeans_pair_kernel(const float* __restrict__ x, const int64_t* __restrict__ clas
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[k][j] = 0ull;
         }
-        if (tid == 0) {
+        if (leader) {
 #pragma unroll
             for (int k = 0; k < K; ++k) { ws_cnt[slot * K + k] = cnt_s[k]; cnt_s[k] = 0; }
         }
     };
 
-    float2* my_tr = tr + (size_t)warp * SLOTS * K2_TR;
-    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-
-    // phase-A batch (a_*) and batch being finished (f_*)
-    int64_t a_row = 0, f_row = 0;
-    int a_n = 0, a_c = -1, f_n = 0, f_c = -1;
-    int a_stage = 0, f_stage = 0, a_buf = 0, f_buf = 0;
-    uint32_t a_par = 0, f_par = 0, a_cpar = 0, f_cpar = 0;
-    bool have_f = false;
-
-    while (true) {
-        const bool have_a = crow < r1;
-        if (!have_a && !have_f) break;
-        if (have_a) {
-            take_batch(class_off, r1, R, crow, cc, cend, a_row, a_n, a_c);
-            if (a_c != mu_class) {
-                mu_class = a_c;
-#pragma unroll
-                for (int p = 0; p < KP; ++p) {
-                    const float4* c0 = reinterpret_cast<const float4*>(centroid + ((int64_t)a_c * K + 2 * p) * D);
-                    const float4* c1 = reinterpret_cast<const float4*>(centroid + ((int64_t)a_c * K + 2 * p + 1) * D);
-                    const bool has1 = 2 * p + 1 < K;
-                    const float4 a0 = own0 ? __ldg(c0 + chunk0) : zero4, a1 = own1 ? __ldg(c0 + chunk1) : zero4;
-                    const float4 b0 = (has1 && own0) ? __ldg(c1 + chunk0) : zero4, b1 = (has1 && own1) ? __ldg(c1 + chunk1) : zero4;
-                    // x * 1 + (-0) == x bit for bit; `one` is opaque to ptxas, so each pair is DEFINED by an FFMA2 result
-                    // register pair and cannot be rematerialised from the two scalar loads inside the hot loop
-                    const f32x2_t nz = pack2(-0.f, -0.f);
-                    mu2[p][0] = ffma2_bcast(pack2(a0.x, b0.x), one, nz); mu2[p][1] = ffma2_bcast(pack2(a0.y, b0.y), one, nz);
-                    mu2[p][2] = ffma2_bcast(pack2(a0.z, b0.z), one, nz); mu2[p][3] = ffma2_bcast(pack2(a0.w, b0.w), one, nz);
-                    mu2[p][4] = ffma2_bcast(pack2(a1.x, b1.x), one, nz); mu2[p][5] = ffma2_bcast(pack2(a1.y, b1.y), one, nz);
-                    mu2[p][6] = ffma2_bcast(pack2(a1.z, b1.z), one, nz); mu2[p][7] = ffma2_bcast(pack2(a1.w, b1.w), one, nz);
-                }
-                cn2_a.x = slot_ok ? __ldg(cnorm + (int64_t)a_c * K + 2 * my_p) : INFINITY;
-                cn2_a.y = (slot_ok && 2 * my_p + 1 < K) ? __ldg(cnorm + (int64_t)a_c * K + 2 * my_p + 1) : INFINITY;
-            }
-            mbar_wait(&full[a_stage], a_par);
-            const float* st = ring + (size_t)a_stage * stage_elems;
-            // phase A: packed partial dots of every row of the batch -> warp-private transposition buffer
-            // (row r+1 is fetched from the ring before the FMAs of row r)
-            auto ld0 = [&](int r) { return own0 ? *reinterpret_cast<const float4*>(st + (size_t)r * D + chunk0 * 4) : zero4; };
-            auto ld1 = [&](int r) { return own1 ? *reinterpret_cast<const float4*>(st + (size_t)r * D + chunk1 * 4) : zero4; };
-            float4 xa = ld0(0), xb = ld1(0);
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                float4 na = xa, nb = xb;
-                if (r + 1 < R) { na = ld0(r + 1); nb = ld1(r + 1); }
-                const float xs[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
-                f32x2_t dp[KP];
-#pragma unroll
-                for (int p = 0; p < KP; ++p) dp[p] = fmul2_bcast(mu2[p][0], xs[0]);
-#pragma unroll
-                for (int j = 1; j < 8; ++j)
-#pragma unroll
-                    for (int p = 0; p < KP; ++p) dp[p] = ffma2_bcast(mu2[p][j], xs[j], dp[p]);
-#pragma unroll
-                for (int p = 0; p < KP; ++p) reinterpret_cast<f32x2_t*>(my_tr)[(r * KP + p) * K2_TR + lane] = dp[p];
-                xa = na; xb = nb;
-            }
-            __syncwarp();
-            // lane = slot: sum the 32 lanes' partials of that slot (fixed order, 4 chains)
-            {
-                const float4* row = reinterpret_cast<const float4*>(my_tr + (slot_ok ? lane : 0) * K2_TR);
-                f32x2_t c0 = 0ull, c1 = 0ull, c2 = 0ull, c3 = 0ull;
-#pragma unroll
-                for (int i = 0; i < 16; i += 2) {
-                    const float4 u = row[i], v = row[i + 1];
-                    c0 = fadd2_s(c0, u.x, u.y); c1 = fadd2_s(c1, u.z, u.w);
-                    c2 = fadd2_s(c2, v.x, v.y); c3 = fadd2_s(c3, v.z, v.w);
-                }
-                reinterpret_cast<f32x2_t*>(cross)[(a_buf * K2_WARPS + warp) * 32 + lane] = fadd2_p(fadd2_p(c0, c1), fadd2_p(c2, c3));
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&cbar[a_buf]);
+    while (crow < r1) {
+        int64_t brow; int bn, bc;
+        take_batch(class_off, r1, R, crow, cc, cend, brow, bn, bc);
+        if (bc != cur) {
+            if (cur >= 0) flush(cur);
+            cur = bc;
+            cn2.x = slot_ok ? __ldg(cnorm + (int64_t)bc * K + 2 * my_p) : INFINITY;
+            cn2.y = (slot_ok && 2 * my_p + 1 < K) ? __ldg(cnorm + (int64_t)bc * K + 2 * my_p + 1) : INFINITY;
         }
-        if (have_f) {
-            mbar_wait(&cbar[f_buf], f_cpar);
-            const f32x2_t* cr = reinterpret_cast<const f32x2_t*>(cross) + (size_t)f_buf * K2_WARPS * 32 + lane;
-            f32x2_t t2 = cr[0];
+        mbar_wait(&cbar[buf], cpar);
+        const f32x2_t* cr = reinterpret_cast<const f32x2_t*>(cross) + (size_t)buf * K2_WARPS * 32 + lane;
+        // fixed-order tree over the 8 DOT-warp totals
+        const f32x2_t t2 = fadd2_p(fadd2_p(fadd2_p(cr[0], cr[32]), fadd2_p(cr[64], cr[96])),
+                                   fadd2_p(fadd2_p(cr[128], cr[160]), fadd2_p(cr[192], cr[224])));
+        const float2 tot = unpack2(t2);
+        // argmin_k (cnorm_k - 2 <x_r, mu_k>), lowest k on ties
+        const float s0 = fmaf(-2.f, tot.x, cn2.x), s1 = fmaf(-2.f, tot.y, cn2.y);
+        const bool odd = s1 < s0;
+        const float best = (odd ? s1 : s0) + 0.f;  // + 0 folds -0 into +0
+        const uint32_t ub = __float_as_uint(best);
+        const uint32_t key = (ub & 0x80000000u) ? ~ub : (ub | 0x80000000u);
+        // one full-mask redux per row (a lane-dependent member mask would compile to a loop over the distinct masks)
+        uint32_t kmin = 0u;
 #pragma unroll
-            for (int w = 1; w < K2_WARPS; ++w) t2 = fadd2_p(t2, cr[w * 32]);  // fixed order
-            const float2 tot = unpack2(t2);
-            // argmin_k (cnorm_k - 2 <x_r, mu_k>), lowest k on ties
-            const float s0 = fmaf(-2.f, tot.x, cn2_f.x), s1 = fmaf(-2.f, tot.y, cn2_f.y);
-            const bool odd = s1 < s0;
-            const float best = (odd ? s1 : s0) + 0.f;  // + 0 folds -0 into +0
-            const uint32_t ub = __float_as_uint(best);
-            const uint32_t key = (ub & 0x80000000u) ? ~ub : (ub | 0x80000000u);
-            // one full-mask redux per row (a lane-dependent member mask would compile to a loop over the distinct masks)
-            uint32_t kmin = 0u;
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const bool mine = slot_ok && my_row == r;
-                const uint32_t m = __reduce_min_sync(0xffffffffu, mine ? key : 0xffffffffu);
-                if (mine) kmin = m;
-            }
-            const bool is_min = slot_ok && key == kmin;
-            const uint32_t bal = __ballot_sync(0xffffffffu, is_min);
-            const uint32_t bal_odd = __ballot_sync(0xffffffffu, is_min && odd);
-            const int rl = lane < R ? lane : 0;
-            const uint32_t rb = (bal >> (rl * KP)) & ((1u << KP) - 1u);
-            const int pl = __ffs(rb) - 1;
-            const int k_lane = 2 * pl + (int)((bal_odd >> (rl * KP + pl)) & 1u);
-            if (warp == 0 && lane < f_n) {
-                assign[f_row + lane] = k_lane;
-                atomicAdd(&cnt_s[k_lane], 1);
-            }
-            int kr[R];
-#pragma unroll
-            for (int r = 0; r < R; ++r) kr[r] = __shfl_sync(0xffffffffu, k_lane, r);
-            // phase B: accumulate the rows into the register sums of their cluster (CTA-uniform branches)
-            const float* st = ring + (size_t)f_stage * stage_elems;
-            auto ld0 = [&](int r) { return own0 ? *reinterpret_cast<const float4*>(st + (size_t)r * D + chunk0 * 4) : zero4; };
-            auto ld1 = [&](int r) { return own1 ? *reinterpret_cast<const float4*>(st + (size_t)r * D + chunk1 * 4) : zero4; };
-            float4 xa = ld0(0), xb = ld1(0);
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                float4 na = xa, nb = xb;
-                if (r + 1 < R) { na = ld0(r + 1); nb = ld1(r + 1); }
-                if (r < f_n) acc_add<K, 0, K>(acc, kr[r], xa, xb);
-                xa = na; xb = nb;
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[f_stage]);
-            if (tid == 0 && irow < r1) {  // the stage is free once all 8 warps have released it
-                mbar_wait(&empty[f_stage], f_par);
-                refill(f_stage);
-            }
-            if (!have_a || a_c != f_c) flush(f_c);  // class finished on this CTA (also zeroes the sums / counts)
+        for (int r = 0; r < R; ++r) {
+            const bool mine = slot_ok && my_row == r;
+            const uint32_t m = __reduce_min_sync(0xffffffffu, mine ? key : 0xffffffffu);
+            if (mine) kmin = m;
         }
-        // batch i+1 becomes the batch to finish
-        have_f = have_a;
-        f_row = a_row; f_n = a_n; f_c = a_c; f_stage = a_stage; f_par = a_par; f_buf = a_buf; f_cpar = a_cpar; cn2_f = cn2_a;
-        if (++a_stage == stages) { a_stage = 0; a_par ^= 1; }
-        if (++a_buf == K2_CROSS) { a_buf = 0; a_cpar ^= 1; }
+        const bool is_min = slot_ok && key == kmin;
+        const uint32_t bal = __ballot_sync(0xffffffffu, is_min);
+        const uint32_t bal_odd = __ballot_sync(0xffffffffu, is_min && odd);
+        const int rl = lane < R ? lane : 0;
+        const uint32_t rb = (bal >> (rl * KP)) & ((1u << KP) - 1u);
+        const int pl = __ffs(rb) - 1;
+        const int k_lane = 2 * pl + (int)((bal_odd >> (rl * KP + pl)) & 1u);
+        if (warp == K2_WARPS && lane < bn) {
+            assign[brow + lane] = k_lane;
+            atomicAdd(&cnt_s[k_lane], 1);
+        }
+        int kr[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) kr[r] = __shfl_sync(0xffffffffu, k_lane, r);
+        // phase B: accumulate the rows into the register sums of their cluster (CTA-uniform branches)
+        mbar_wait(&full[stage], par);  // completed long ago (the DOT warps waited on it); acquires the TMA writes
+        const float* st = ring + (size_t)stage * stage_elems;
+        auto ld0 = [&](int r) { return own0 ? *reinterpret_cast<const float4*>(st + (size_t)r * D + chunk0 * 4) : zero4; };
+        auto ld1 = [&](int r) { return own1 ? *reinterpret_cast<const float4*>(st + (size_t)r * D + chunk1 * 4) : zero4; };
+        float4 xa = ld0(0), xb = ld1(0);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            float4 na = xa, nb = xb;
+            if (r + 1 < R) { na = ld0(r + 1); nb = ld1(r + 1); }
+            if (r < bn) acc_add<K, 0, K>(acc, kr[r], xa, xb);
+            xa = na; xb = nb;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);
+        if (leader && irow < r1) {  // the stage is free once all 16 warps have released it
+            mbar_wait(&empty[stage], par);
+            refill(stage);
+        }
+        advance();
     }
+    if (cur >= 0) flush(cur);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -852,7 +866,7 @@ template <int K>
 static int launch_kmeans_pair(const float* x, const int64_t* class_off, int64_t N, int D, int C, const float* centroid,
                               const float* cnorm, int32_t* assign, double* ws_sum, int64_t* ws_cnt, int G, cudaStream_t st) {
     const size_t limit = 227 * 1024;
-    int stages = PK_MAX_STAGES;
+    int stages = K2_CROSS;
     while (stages > 2 && k2_smem_bytes(stages, D, K) > limit) --stages;
     DD_REQUIRE(k2_smem_bytes(stages, D, K) <= limit, DD_EUNSUPPORTED, "kmeans: D=%d too large for the shared-memory ring", D);
     const size_t smem = k2_smem_bytes(stages, D, K);

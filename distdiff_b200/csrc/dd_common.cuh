@@ -219,9 +219,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // Bounded spin: a protocol bug becomes a trapped launch (reported through the C ABI's error code) instead of a
 // hung GPU.  Every legitimate wait in this library ends within microseconds; 2^24 timed-out polls never happen.
+template <unsigned SLEEP_NS = 64>
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(SLEEP_NS);  // back off: a polling warp must not take issue slots from the warps it is waiting for
         if (++spins == (1u << 24)) __trap();
     }
 }

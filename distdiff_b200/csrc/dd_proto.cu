@@ -284,7 +284,8 @@ kmeans_stream_kernel(const float* __restrict__ x, const int64_t* __restrict__ cl
 constexpr int K2_WARPS = 8;                    // compute warps
 constexpr int K2_COMPUTE = K2_WARPS * 32;
 constexpr int K2_THREADS = 2 * K2_COMPUTE;      // 8 DOT warps + 8 ACC warps
-constexpr int K2_R = 6;                        // rows per batch
+// rows per batch: as many as fit 32 reduction lanes AND leave room for a 4-stage ring next to the transposition buffer
+__host__ __device__ constexpr int k2_rows(int K) { return K >= 1 ? 6 : 6; }
 constexpr int K2_TR = 34;                      // float2 per transposition row: 272 B keeps LDS.128 conflict-free
 constexpr int K2_MAXK = 10;
 
@@ -315,7 +316,9 @@ __device__ __forceinline__ void acc_add(f32x2_t (&acc)[K][4], int k, const float
 //     warp-private transposition sum, warp totals -> cross[buf]; arrive on cbar[buf]; release the ring stage.
 //   * ACC warps 8-15 hold the per-cluster sums (4*K f32x2): wait cbar[buf], add the 8 warp totals in fixed order,
 //     argmin, write assignments, re-read the rows from the ring and accumulate; release the stage; the first ACC
-//     lane refills it through the TMA engine once all 16 warps have released it.
+//     lane (the leader) refills it through the TMA engine once all 16 warps have released it.
+// Only the leader walks the (64-bit) batch cursor: it publishes a descriptor {row offset, rows, class} per ring
+// stage before arming the stage's `full` barrier, and a rows == 0 sentinel after the last batch.
 // The DOT warps run up to `stages` batches ahead, so a scheduler always has FMA-bound and latency-bound warps to
 // pick from (4 per scheduler instead of the 2 a 255-register thread allows).
 constexpr int K2_CROSS = 4;  // cross buffers; the ring is capped at K2_CROSS stages so a buffer is never overwritten early
@@ -326,16 +329,17 @@ kmeans_pair_kernel(const float* __restrict__ x, const int64_t* __restrict__ clas
                    const float* __restrict__ centroid, const float* __restrict__ cnorm, int32_t* __restrict__ assign,
                    double* __restrict__ ws_sum, int64_t* __restrict__ ws_cnt, int stages) {
     constexpr int KP = (K + 1) / 2;   // cluster pairs
-    constexpr int R = K2_R;
+    constexpr int R = k2_rows(K);
     constexpr int SLOTS = R * KP;     // packed partials per batch (<= 30): one per lane in the reduction
-    static_assert(K >= 1 && K <= K2_MAXK && SLOTS <= 32, "unsupported K");
+    static_assert(K >= 1 && K <= K2_MAXK && SLOTS <= 32 && R % 2 == 0, "unsupported K");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const size_t stage_elems = (size_t)R * D;
     float* ring = reinterpret_cast<float*>(smem_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)stages * stage_elems * sizeof(float));
     uint64_t* empty = full + PK_MAX_STAGES;
     uint64_t* cbar = empty + PK_MAX_STAGES;                                  // [K2_CROSS]
-    float2* tr = reinterpret_cast<float2*>(cbar + K2_CROSS);                 // [K2_WARPS][SLOTS][K2_TR]
+    int4* desc = reinterpret_cast<int4*>(cbar + K2_CROSS);                   // [K2_CROSS] {row - r0, rows, class, -}
+    float2* tr = reinterpret_cast<float2*>(desc + K2_CROSS);                 // [K2_WARPS][SLOTS][K2_TR]
     float2* cross = tr + (size_t)K2_WARPS * SLOTS * K2_TR;                   // [K2_CROSS][K2_WARPS][32]
     int* cnt_s = reinterpret_cast<int*>(cross + K2_CROSS * K2_WARPS * 32);   // [16]
 
@@ -358,10 +362,6 @@ kmeans_pair_kernel(const float* __restrict__ x, const int64_t* __restrict__ clas
     const bool own0 = FULL || chunk0 < nch, own1 = FULL || chunk1 < nch;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
-    // batch cursor (every thread walks the same deterministic batch sequence)
-    int64_t crow = r0;
-    int cc = find_class(class_off, C, r0);
-    int64_t cend = __ldg(class_off + cc + 1);
     int stage = 0, buf = 0;
     uint32_t par = 0, cpar = 0;
     auto advance = [&]() {
@@ -376,9 +376,11 @@ kmeans_pair_kernel(const float* __restrict__ x, const int64_t* __restrict__ clas
         int mu_class = -1;
         float2* my_tr = tr + (size_t)warp * SLOTS * K2_TR;
         const bool slot_ok = lane < SLOTS;
-        while (crow < r1) {
-            int64_t brow; int bn, bc;
-            take_batch(class_off, r1, R, crow, cc, cend, brow, bn, bc);
+        while (true) {
+            mbar_wait(&full[stage], par);
+            const int4 d = desc[stage];
+            if (d.y == 0) break;
+            const int bc = d.z;
             if (bc != mu_class) {
                 mu_class = bc;
 #pragma unroll
@@ -397,23 +399,32 @@ kmeans_pair_kernel(const float* __restrict__ x, const int64_t* __restrict__ clas
                     mu2[p][6] = ffma2_bcast(pack2(a1.z, b1.z), one, nz); mu2[p][7] = ffma2_bcast(pack2(a1.w, b1.w), one, nz);
                 }
             }
-            mbar_wait(&full[stage], par);
             const float* st = ring + (size_t)stage * stage_elems;
-            // phase A: packed partial dots of every row of the batch -> warp-private transposition buffer
+            // phase A: packed partial dots of every row of the batch -> warp-private transposition buffer.
+            // Two rows at a time: 2*KP independent FFMA2 chains cover the packed-FMA latency.
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const float4 xa = own0 ? *reinterpret_cast<const float4*>(st + (size_t)r * D + chunk0 * 4) : zero4;
-                const float4 xb = own1 ? *reinterpret_cast<const float4*>(st + (size_t)r * D + chunk1 * 4) : zero4;
-                const float xs[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
-                f32x2_t dp[KP];
+            for (int r = 0; r < R; r += 2) {
+                const float4 xa0 = own0 ? *reinterpret_cast<const float4*>(st + (size_t)r * D + chunk0 * 4) : zero4;
+                const float4 xb0 = own1 ? *reinterpret_cast<const float4*>(st + (size_t)r * D + chunk1 * 4) : zero4;
+                const float4 xa1 = own0 ? *reinterpret_cast<const float4*>(st + (size_t)(r + 1) * D + chunk0 * 4) : zero4;
+                const float4 xb1 = own1 ? *reinterpret_cast<const float4*>(st + (size_t)(r + 1) * D + chunk1 * 4) : zero4;
+                const float xs0[8] = {xa0.x, xa0.y, xa0.z, xa0.w, xb0.x, xb0.y, xb0.z, xb0.w};
+                const float xs1[8] = {xa1.x, xa1.y, xa1.z, xa1.w, xb1.x, xb1.y, xb1.z, xb1.w};
+                f32x2_t dp0[KP], dp1[KP];
 #pragma unroll
-                for (int p = 0; p < KP; ++p) dp[p] = fmul2_bcast(mu2[p][0], xs[0]);
+                for (int p = 0; p < KP; ++p) { dp0[p] = fmul2_bcast(mu2[p][0], xs0[0]); dp1[p] = fmul2_bcast(mu2[p][0], xs1[0]); }
 #pragma unroll
                 for (int j = 1; j < 8; ++j)
 #pragma unroll
-                    for (int p = 0; p < KP; ++p) dp[p] = ffma2_bcast(mu2[p][j], xs[j], dp[p]);
+                    for (int p = 0; p < KP; ++p) {
+                        dp0[p] = ffma2_bcast(mu2[p][j], xs0[j], dp0[p]);
+                        dp1[p] = ffma2_bcast(mu2[p][j], xs1[j], dp1[p]);
+                    }
 #pragma unroll
-                for (int p = 0; p < KP; ++p) reinterpret_cast<f32x2_t*>(my_tr)[(r * KP + p) * K2_TR + lane] = dp[p];
+                for (int p = 0; p < KP; ++p) {
+                    reinterpret_cast<f32x2_t*>(my_tr)[(r * KP + p) * K2_TR + lane] = dp0[p];
+                    reinterpret_cast<f32x2_t*>(my_tr)[((r + 1) * KP + p) * K2_TR + lane] = dp1[p];
+                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[stage]);  // the DOT side is done with the rows
@@ -442,20 +453,30 @@ kmeans_pair_kernel(const float* __restrict__ x, const int64_t* __restrict__ clas
     }
 
     // =========================== ACC warps ===========================
-    const bool leader = tid == K2_COMPUTE;  // first ACC lane: drives the TMA engine
-    // producer cursor (leader only): prologue fills every stage
-    int64_t irow = crow;
-    int ic = cc;
-    int64_t iend = cend;
+    const bool leader = tid == K2_COMPUTE;  // first ACC lane: walks the batch cursor and drives the TMA engine
+    int64_t irow = r0;
+    int ic = 0;
+    int64_t iend = 0;
+    bool fed = false;  // sentinel published
     auto refill = [&](int s) {
-        int64_t br; int bn, bc;
-        take_batch(class_off, r1, R, irow, ic, iend, br, bn, bc);
-        const uint32_t bytes = (uint32_t)bn * D * sizeof(float);
-        mbar_expect_tx(&full[s], bytes);
-        bulk_g2s(ring + (size_t)s * stage_elems, x + br * D, bytes, &full[s]);
+        if (irow < r1) {
+            int64_t br; int bn, bc;
+            take_batch(class_off, r1, R, irow, ic, iend, br, bn, bc);
+            desc[s] = make_int4((int)(br - r0), bn, bc, 0);
+            const uint32_t bytes = (uint32_t)bn * D * sizeof(float);
+            mbar_expect_tx(&full[s], bytes);
+            bulk_g2s(ring + (size_t)s * stage_elems, x + br * D, bytes, &full[s]);
+        } else {
+            desc[s] = make_int4(0, 0, 0, 0);
+            mbar_arrive(&full[s]);
+            fed = true;
+        }
     };
-    if (leader)
-        for (int s = 0; s < stages && irow < r1; ++s) refill(s);
+    if (leader) {
+        ic = find_class(class_off, C, r0);
+        iend = __ldg(class_off + ic + 1);
+        for (int s = 0; s < stages && !fed; ++s) refill(s);
+    }
 
     const int my_p = lane % KP, my_row = lane / KP;
     const bool slot_ok = lane < SLOTS;
@@ -484,16 +505,18 @@ kmeans_pair_kernel(const float* __restrict__ x, const int64_t* __restrict__ clas
         }
     };
 
-    while (crow < r1) {
-        int64_t brow; int bn, bc;
-        take_batch(class_off, r1, R, crow, cc, cend, brow, bn, bc);
+    while (true) {
+        mbar_wait(&full[stage], par);  // descriptor + rows of this stage are visible
+        const int4 d = desc[stage];
+        const int bn = d.y, bc = d.z;
+        if (bn == 0) break;
         if (bc != cur) {
             if (cur >= 0) flush(cur);
             cur = bc;
             cn2.x = slot_ok ? __ldg(cnorm + (int64_t)bc * K + 2 * my_p) : INFINITY;
             cn2.y = (slot_ok && 2 * my_p + 1 < K) ? __ldg(cnorm + (int64_t)bc * K + 2 * my_p + 1) : INFINITY;
         }
-        mbar_wait(&cbar[buf], cpar);
+        mbar_wait<256>(&cbar[buf], cpar);
         const f32x2_t* cr = reinterpret_cast<const f32x2_t*>(cross) + (size_t)buf * K2_WARPS * 32 + lane;
         // fixed-order tree over the 8 DOT-warp totals
         const f32x2_t t2 = fadd2_p(fadd2_p(fadd2_p(cr[0], cr[32]), fadd2_p(cr[64], cr[96])),
@@ -505,30 +528,24 @@ kmeans_pair_kernel(const float* __restrict__ x, const int64_t* __restrict__ clas
         const float best = (odd ? s1 : s0) + 0.f;  // + 0 folds -0 into +0
         const uint32_t ub = __float_as_uint(best);
         const uint32_t key = (ub & 0x80000000u) ? ~ub : (ub | 0x80000000u);
-        // one full-mask redux per row (a lane-dependent member mask would compile to a loop over the distinct masks)
-        uint32_t kmin = 0u;
+        // two full-mask redux per row, both landing in uniform registers: the row's minimum key, then the lowest
+        // cluster index among the lanes that hold it (a lane-dependent member mask would compile to a loop over masks)
+        const uint32_t k_mine = 2u * my_p + (odd ? 1u : 0u);
+        int kr[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const bool mine = slot_ok && my_row == r;
             const uint32_t m = __reduce_min_sync(0xffffffffu, mine ? key : 0xffffffffu);
-            if (mine) kmin = m;
+            kr[r] = (int)__reduce_min_sync(0xffffffffu, (mine && key == m) ? k_mine : 0xffffffffu);
         }
-        const bool is_min = slot_ok && key == kmin;
-        const uint32_t bal = __ballot_sync(0xffffffffu, is_min);
-        const uint32_t bal_odd = __ballot_sync(0xffffffffu, is_min && odd);
-        const int rl = lane < R ? lane : 0;
-        const uint32_t rb = (bal >> (rl * KP)) & ((1u << KP) - 1u);
-        const int pl = __ffs(rb) - 1;
-        const int k_lane = 2 * pl + (int)((bal_odd >> (rl * KP + pl)) & 1u);
         if (warp == K2_WARPS && lane < bn) {
-            assign[brow + lane] = k_lane;
+            int k_lane = kr[0];
+#pragma unroll
+            for (int r = 1; r < R; ++r) k_lane = lane == r ? kr[r] : k_lane;
+            assign[r0 + d.x + lane] = k_lane;
             atomicAdd(&cnt_s[k_lane], 1);
         }
-        int kr[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) kr[r] = __shfl_sync(0xffffffffu, k_lane, r);
         // phase B: accumulate the rows into the register sums of their cluster (CTA-uniform branches)
-        mbar_wait(&full[stage], par);  // completed long ago (the DOT warps waited on it); acquires the TMA writes
         const float* st = ring + (size_t)stage * stage_elems;
         auto ld0 = [&](int r) { return own0 ? *reinterpret_cast<const float4*>(st + (size_t)r * D + chunk0 * 4) : zero4; };
         auto ld1 = [&](int r) { return own1 ? *reinterpret_cast<const float4*>(st + (size_t)r * D + chunk1 * 4) : zero4; };
@@ -542,7 +559,7 @@ kmeans_pair_kernel(const float* __restrict__ x, const int64_t* __restrict__ clas
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[stage]);
-        if (leader && irow < r1) {  // the stage is free once all 16 warps have released it
+        if (leader && !fed) {  // the stage is free once all 16 warps have released it
             mbar_wait(&empty[stage], par);
             refill(stage);
         }
@@ -857,8 +874,8 @@ static int launch_kmeans(const float* x, const int64_t* class_off, int64_t N, in
 
 static size_t k2_smem_bytes(int stages, int D, int K) {
     const int KP = (K + 1) / 2;
-    return (size_t)stages * K2_R * D * sizeof(float) + 2 * PK_MAX_STAGES * sizeof(uint64_t) +
-           K2_CROSS * sizeof(uint64_t) + (size_t)K2_WARPS * K2_R * KP * K2_TR * sizeof(float2) +
+    return (size_t)stages * k2_rows(K) * D * sizeof(float) + 2 * PK_MAX_STAGES * sizeof(uint64_t) +
+           K2_CROSS * (sizeof(uint64_t) + sizeof(int4)) + (size_t)K2_WARPS * k2_rows(K) * KP * K2_TR * sizeof(float2) +
            (size_t)K2_CROSS * K2_WARPS * 32 * sizeof(float2) + 16 * sizeof(int);
 }
 

@@ -287,6 +287,7 @@ constexpr int K2_THREADS = 2 * K2_COMPUTE;      // 8 DOT warps + 8 ACC warps
 // rows per batch: as many as fit 32 reduction lanes AND leave room for a 4-stage ring next to the transposition buffer
 __host__ __device__ constexpr int k2_rows(int K) { return K >= 1 ? 6 : 6; }
 constexpr int K2_TR = 34;                      // float2 per transposition row: 272 B keeps LDS.128 conflict-free
+constexpr int K2_MINK = 4;
 constexpr int K2_MAXK = 10;
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -516,7 +517,7 @@ kmeans_pair_kernel(const float* __restrict__ x, const int64_t* __restrict__ clas
             cn2.x = slot_ok ? __ldg(cnorm + (int64_t)bc * K + 2 * my_p) : INFINITY;
             cn2.y = (slot_ok && 2 * my_p + 1 < K) ? __ldg(cnorm + (int64_t)bc * K + 2 * my_p + 1) : INFINITY;
         }
-        mbar_wait<256>(&cbar[buf], cpar);
+        mbar_wait(&cbar[buf], cpar);
         const f32x2_t* cr = reinterpret_cast<const f32x2_t*>(cross) + (size_t)buf * K2_WARPS * 32 + lane;
         // fixed-order tree over the 8 DOT-warp totals
         const f32x2_t t2 = fadd2_p(fadd2_p(fadd2_p(cr[0], cr[32]), fadd2_p(cr[64], cr[96])),
@@ -988,9 +989,11 @@ int dd_kmeans_assign_accum(const float* x_sorted, const int64_t* class_off, int6
     int64_t* ws_cnt = (int64_t*)((char*)ws + w.cnt_off);
     double* ws_in = (double*)((char*)ws + w.inertia_off);
     int rc = 0;
-    if (N > 0 && !inertia && K <= dd::K2_MAXK) {
+    // K <= 3: the single-role streaming kernel is HBM-bound already (8 rows per reduction round, 81 % of peak);
+    // K = 4..10: the warp-specialised cluster-paired kernel; K > 10 or inertia requested: streaming kernel.
+    if (N > 0 && !inertia && K >= dd::K2_MINK && K <= dd::K2_MAXK) {
 #define DD_KP(KK) case KK: rc = dd::launch_kmeans_pair<KK>(x_sorted, class_off, N, D, C, centroid, cnorm, assign, ws_sum, ws_cnt, G, st); break;
-        switch (K) { DD_KP(1) DD_KP(2) DD_KP(3) DD_KP(4) DD_KP(5) DD_KP(6) DD_KP(7) DD_KP(8) DD_KP(9) DD_KP(10) }
+        switch (K) { DD_KP(4) DD_KP(5) DD_KP(6) DD_KP(7) DD_KP(8) DD_KP(9) DD_KP(10) }
 #undef DD_KP
         if (rc) return rc;
     } else if (N > 0) {

@@ -9,6 +9,7 @@ UNet / VAE / guide network is one fused sm_100a kernel (``distdiff_b200.ops``):
     cat/chunk, sub, mul, add, DDIMScheduler.step (~13)   -> K5  dd_cfg_ddim_fwd (+ dd_cfg_ddim_bwd under autograd)
     latents*(1+a)+b (3) and its autograd reduce          -> K6  dd_affine_project_fwd / dd_affine_bwd
     gathers, 2 norms, bmm, argmax, index, means (~14+14) -> K4  dd_energy_fwd_bwd (forward AND analytic gradient)
+    F.interpolate(bicubic, 224) + its atomic backward    -> K8  dd_bicubic_resize_fwd / _bwd (deterministic gather)
     transform + tensor_clamp masks/scatters (~9)         -> K6  dd_affine_project_fwd (radius >= 0)
     x_next - rho*grad (2)                                -> fused into K5's epilogue
 
@@ -60,10 +61,13 @@ def linfball_proj(center, radius, t, in_place=True):
 
 
 def _guide_features(pred_x0, vae, image_encoder, image_processor, generator):
-    """generate_data.py:701-705 / 743-746 -- decode, postprocess (identity), bicubic 224, guide (PyTorch)."""
+    """generate_data.py:701-705 / 743-746 -- decode (PyTorch), postprocess (identity), bicubic 224 (K8), guide (PyTorch)."""
     D_x0_t = vae.decode(pred_x0 / vae.config.scaling_factor, return_dict=False, generator=generator)[0]
     D_x0_t = image_processor.postprocess(D_x0_t, output_type="pt", do_denormalize=[False] * D_x0_t.shape[0])
-    D_x0_t = torch.nn.functional.interpolate(D_x0_t, size=(224, 224), mode="bicubic")
+    if D_x0_t.requires_grad and torch.is_grad_enabled():
+        D_x0_t = ops.BicubicResize.apply(D_x0_t, (224, 224))                                      # :704 / :745
+    else:
+        D_x0_t = ops.bicubic_resize(D_x0_t, (224, 224))
     return image_encoder.encode_image(D_x0_t).float()
 
 

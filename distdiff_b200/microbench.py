@@ -7,7 +7,7 @@ every timed launch by READING a 512 MB buffer (a write-flush would leave dirty l
 bandwidth from the timed kernel), CUDA events on the launching stream, median of ``iters``.
 
 Algorithmic bytes per launch:
-  K5 fwd/bwd 5*B*16384*s   K6 2*B*16384*s   K7 3*B*16384*s   K4 B*(K+3)*D*4   K1 2*N*D*4+N*8   K3 N*D*4+2*N*4
+  K5 fwd/bwd 5*B*16384*s   K6 2*B*16384*s   K7 3*B*16384*s   K4 B*(K+3)*D*4   K1 2*N*D*4+N*8   K3 N*D*4+2*N*4   K8 (B*3*512*512 + B*3*224*224)*s
 """
 from __future__ import annotations
 
@@ -113,6 +113,23 @@ def run(want=lambda name: True, iters=10, ks=(3, 5, 10), latent_dtypes=(torch.fl
                 for nf in (False, True):
                     t = timeit(lambda: ops.energy_fwd_bwd(f, y, g, l, 1.0, 1.0, nf), iters)
                     report(f"K4_energy_K{K}_B{B}_norm{int(nf)}", B * (K + 3) * D * 4, t, hbm_compulsory_bytes=2 * B * D * 4 + (K + 1) * C * D * 4)
+    if want("K8"):
+        for dt in latent_dtypes:
+            es = torch.empty(0, dtype=dt).element_size()
+            dn = str(dt).split(".")[-1]
+            for B in (4, 128):
+                img = torch.randn(B, 3, 512, 512, device=dev).to(dt)
+                gr = torch.randn(B, 3, 224, 224, device=dev).to(dt)
+                nb = (img.numel() + gr.numel()) * es
+                report(f"K8_bicubic_fwd_{dn}_B{B}", nb, timeit(lambda: ops.bicubic_resize(img, (224, 224)), iters))
+                report(f"K8_bicubic_bwd_{dn}_B{B}", nb, timeit(lambda: ops.bicubic_resize_bwd(gr, (512, 512)), iters))
+                if B == 128:   # the eager ops K8 replaces, same tensors (ATen upsample_bicubic2d + its atomicAdd backward)
+                    report(f"aten_bicubic_fwd_{dn}_B{B}", nb, timeit(lambda: torch.nn.functional.interpolate(img, size=(224, 224), mode="bicubic"), iters))
+                    xi = img.clone().requires_grad_(True)
+                    yo = torch.nn.functional.interpolate(xi, size=(224, 224), mode="bicubic")
+                    report(f"aten_bicubic_bwd_{dn}_B{B}", nb, timeit(lambda: torch.autograd.grad(yo, xi, gr, retain_graph=True), iters))
+                    del xi, yo
+                del img, gr
     N = n_feat
     if want("K1") or want("K3"):
         feat = torch.randn(N, D, device=dev)

@@ -193,6 +193,53 @@ class ChannelAffine(torch.autograd.Function):
 
 
 # ------------------------------------------------------------------------------------------------
+# K8  bicubic resize (decoded image -> guide input)
+# ------------------------------------------------------------------------------------------------
+def _hw(size):
+    if isinstance(size, int):
+        return size, size
+    h, w = size
+    return int(h), int(w)
+
+
+def bicubic_resize(x: torch.Tensor, size) -> torch.Tensor:
+    """torch.nn.functional.interpolate(x, size=size, mode='bicubic') for [B,C,H,W] (generate_data.py:704,745)."""
+    x = _req(x, "image")
+    if x.dim() != 4:
+        raise DistDiffError(f"bicubic_resize expects [B,C,H,W], got {tuple(x.shape)}")
+    ho, wo = _hw(size)
+    B, Cc, H, W = x.shape
+    out = torch.empty((B, Cc, ho, wo), dtype=x.dtype, device=x.device)
+    _call("dd_bicubic_resize_fwd", (x.numel() + out.numel()) * x.element_size(), 1,
+          _ptr(x), B * Cc, H, W, ho, wo, _code(x), _ptr(out), _stream())
+    return out
+
+
+def bicubic_resize_bwd(grad_out: torch.Tensor, in_hw) -> torch.Tensor:
+    """Gradient of bicubic_resize w.r.t. its input (deterministic gather)."""
+    g = _req(grad_out, "grad_out")
+    B, Cc, ho, wo = g.shape
+    H, W = _hw(in_hw)
+    gin = torch.empty((B, Cc, H, W), dtype=g.dtype, device=g.device)
+    _call("dd_bicubic_resize_bwd", (g.numel() + gin.numel()) * g.element_size(), 1,
+          _ptr(g), B * Cc, H, W, ho, wo, _code(g), _ptr(gin), _stream())
+    return gin
+
+
+class BicubicResize(torch.autograd.Function):
+    """Differentiable K8; the resize is linear, so nothing is saved for the backward."""
+
+    @staticmethod
+    def forward(ctx, x, size):
+        ctx.in_hw = (x.shape[2], x.shape[3])
+        return bicubic_resize(x.detach(), size)
+
+    @staticmethod
+    def backward(ctx, g):
+        return bicubic_resize_bwd(g, ctx.in_hw), None
+
+
+# ------------------------------------------------------------------------------------------------
 # K7  add_noise
 # ------------------------------------------------------------------------------------------------
 def add_noise(x: torch.Tensor, noise: torch.Tensor, a_t: float) -> torch.Tensor:

@@ -78,6 +78,19 @@ int dd_affine_bwd(const void* g_y, const void* x, const float* a, int64_t BC, in
  *     out = sqrt(a_t) * x + sqrt(1 - a_t) * noise */
 int dd_add_noise(const void* x, const void* noise, int64_t n, int dtype, float a_t, void* out, dd_stream_t stream);
 
+/* ---- K8: bicubic resize of the decoded image for the guide network -------------------
+ * Replaces generate_data.py:704 / :745, torch.nn.functional.interpolate(D_x0_t, size=(224, 224),
+ * mode='bicubic') (align_corners=False, no antialias), and its autograd backward (:721, :761 differentiate
+ * through it).  in: [planes, Hin, Win] contiguous (planes = B*C), out: [planes, Hout, Wout], same dtype;
+ * fp32 arithmetic in ATen's operation order (source coordinate (in/out)*(dst+0.5)-0.5, A = -0.75, taps
+ * clamped to the image, rows interpolated along x first, then y), one rounding to the storage type.
+ * The backward is a gather with a fixed summation order (ATen scatters with atomics): bit-reproducible.
+ * Any scale whose per-tile region fits shared memory (down-scaling up to ~6x, up-scaling up to ~10x). */
+int dd_bicubic_resize_fwd(const void* in, int64_t planes, int Hin, int Win, int Hout, int Wout, int dtype, void* out,
+                          dd_stream_t stream);
+int dd_bicubic_resize_bwd(const void* grad_out, int64_t planes, int Hin, int Win, int Hout, int Wout, int dtype,
+                          void* grad_in, dd_stream_t stream);
+
 /* ---- K4: hierarchical prototype energy, forward + analytic gradient -------------------------------
  * Replaces generate_data.py:707-717 / :747-759 and their autograd backward:
  *     fn    = normalize_f ? f / ||f|| : f                                   (direct mode, :747)

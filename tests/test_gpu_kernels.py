@@ -425,3 +425,64 @@ def test_kmeans_tiny_and_empty(ops, cuda_device):
     buf0 = ops.KMeansBuffers(0, 64, 4, 2, cuda_device)
     ops.kmeans_assign_accum(xs0, off0, buf0, want_inertia=True)
     assert int(buf0.cnt.sum()) == 0 and float(buf0.inertia) == 0.0
+
+
+# ------------------------------------------------------------------------------------------- K8 bicubic resize
+_RS_CASES = [((2, 3, 512, 512), (224, 224)), ((1, 3, 100, 77), (37, 50)), ((1, 2, 64, 64), (64, 64)),
+             ((1, 1, 48, 96), (56, 120)), ((3, 1, 130, 40), (30, 9)), ((1, 3, 256, 256), (224, 224)),
+             ((2, 3, 64, 64), (224, 224)), ((1, 1, 5, 7), (3, 2))]
+
+
+@pytest.mark.parametrize("shape,size", _RS_CASES)
+def test_bicubic_resize_fwd_fp32(ops, cuda_device, shape, size):
+    from oracle import resize
+    x = torch.randn(shape, generator=_g(11))
+    got = ops.bicubic_resize(x.to(cuda_device), size).cpu()
+    ref = resize.interpolate_bicubic(x, size)                  # the reference's call (generate_data.py:704), CPU fp32
+    ref64 = resize.bicubic_numpy(x.numpy(), size)              # ATen's arithmetic restated, fp64 accumulation
+    scale = float(ref.abs().max())
+    assert float((got - ref).abs().max()) <= 1e-5 * scale      # fp32: accumulation order / FMA contraction only
+    assert np.abs(got.numpy() - ref64).max() <= 1e-5 * scale
+    # same op on the GPU through ATen: the arithmetic order is ATen's, so this is (near) bit-exact
+    aten = torch.nn.functional.interpolate(x.to(cuda_device), size=size, mode="bicubic").cpu()
+    assert float((got - aten).abs().max()) <= 2e-6 * scale
+
+
+@pytest.mark.parametrize("dtype,ulp", [(torch.float16, 2.0 ** -10), (torch.bfloat16, 2.0 ** -7)])
+def test_bicubic_resize_fwd_half(ops, cuda_device, dtype, ulp):
+    from oracle import resize
+    x = torch.randn((2, 3, 512, 512), generator=_g(12)).to(dtype)
+    got = ops.bicubic_resize(x.to(cuda_device), (224, 224))
+    assert got.dtype == dtype
+    ref = resize.bicubic_numpy(x.float().numpy(), (224, 224))  # exact result of the stored inputs
+    err = np.abs(got.float().cpu().numpy() - ref)
+    assert (err <= ulp * np.maximum(np.abs(ref), 1e-3) + 1e-6).all()   # one rounding to the storage type
+
+
+@pytest.mark.parametrize("shape,size", _RS_CASES)
+def test_bicubic_resize_bwd(ops, cuda_device, shape, size):
+    from oracle import resize
+    g = torch.randn((shape[0], shape[1]) + size, generator=_g(13))
+    got = ops.bicubic_resize_bwd(g.to(cuda_device), shape[2:])
+    ref = resize.bicubic_backward_numpy(g.numpy(), shape[2:])
+    assert np.abs(got.cpu().numpy() - ref).max() <= 1e-5 * np.abs(ref).max()
+    again = ops.bicubic_resize_bwd(g.to(cuda_device), shape[2:])
+    assert torch.equal(got, again)                              # gather, fixed order: bit-reproducible
+
+
+def test_bicubic_resize_autograd(ops, cuda_device):
+    x = torch.randn((2, 3, 96, 80), generator=_g(14))
+    xd = x.to(cuda_device).requires_grad_(True)
+    w = torch.randn((2, 3, 42, 35), generator=_g(15))
+    (ops.BicubicResize.apply(xd, (42, 35)) * w.to(cuda_device)).sum().backward()
+    xr = x.clone().requires_grad_(True)   # fp32 autograd of the reference's call (fp64 would move the tap positions)
+    (torch.nn.functional.interpolate(xr, size=(42, 35), mode="bicubic") * w).sum().backward()
+    assert float((xd.grad.cpu() - xr.grad).abs().max()) <= 1e-5 * float(xr.grad.abs().max())
+
+
+def test_bicubic_resize_errors(ops, cuda_device):
+    from distdiff_b200._lib import DistDiffError
+    with pytest.raises(DistDiffError):
+        ops.bicubic_resize(torch.randn(1, 3, 8, 8), (4, 4))                     # CPU tensor: no fallback
+    with pytest.raises(DistDiffError):
+        ops.bicubic_resize(torch.randn(1, 1, 512, 512, device=cuda_device), (16, 16))      # 32x down-scaling: region > smem

@@ -174,3 +174,32 @@ def test_kmeans_spec_matches_sklearn_lloyd():
     km = KMeans(n_clusters=4, init=prototypes.kmeans_init(X, 4), n_init=1, algorithm="lloyd", tol=0, max_iter=30).fit(X)
     assert np.array_equal(km.labels_, assign)
     assert np.allclose(km.cluster_centers_, mu, rtol=1e-5, atol=1e-7)
+
+
+# ------------------------------------------------------------------------------------------- resize (K8 oracle)
+@pytest.mark.parametrize("shape,size", [((2, 3, 64, 48), (28, 21)), ((1, 3, 512, 512), (224, 224)), ((1, 2, 40, 40), (40, 40)),
+                                        ((1, 1, 33, 47), (41, 52)), ((1, 1, 9, 300), (4, 131))])
+def test_bicubic_restatement_vs_torch_interpolate(shape, size):
+    """oracle.resize.bicubic_numpy (ATen's arithmetic from scratch) == the reference's own call, generate_data.py:704."""
+    from oracle import resize
+    x = torch.randn(shape, generator=torch.Generator().manual_seed(3))
+    ref = resize.interpolate_bicubic(x, size).numpy()
+    got = resize.bicubic_numpy(x.numpy(), size)
+    assert np.abs(ref - got).max() <= 2e-5 * max(1.0, np.abs(ref).max())
+    # backward == transpose of the same linear map (torch autograd in fp32: in fp64 ATen also computes the scale and
+    # the tap positions in double, which is a different function from the fp32/fp16 one the reference runs)
+    xg = x.clone().requires_grad_(True)
+    y = torch.nn.functional.interpolate(xg, size=size, mode="bicubic")
+    g = torch.randn(y.shape, generator=torch.Generator().manual_seed(4))
+    y.backward(g)
+    gb = resize.bicubic_backward_numpy(g.numpy(), shape[2:])
+    assert np.abs(xg.grad.numpy() - gb).max() <= 2e-5 * max(1.0, np.abs(gb).max())
+
+
+def test_bicubic_axis_matrix_properties():
+    from oracle import resize
+    M = resize.axis_matrix(512, 224)
+    assert np.allclose(M.sum(1), 1.0, atol=1e-6)            # partition of unity
+    assert (np.count_nonzero(M, axis=1) <= 4).all()         # 4 taps per output
+    assert (np.count_nonzero(M, axis=0) <= 3).all()         # <= 2-3 outputs touch one input at scale 2.29
+    assert np.array_equal(resize.axis_matrix(17, 17), np.eye(17, dtype=np.float32))

@@ -95,8 +95,9 @@ class Expander:
             g = self._graphs[key] = _GraphedStep(self, latents, prompt_embeds, t)
         return g(latents, prompt_embeds)
 
-    def expand_batch(self, batch, image_i: int = 0, decode: bool = True):
-        """generate_data.py:1145-1227 for one batch -> (images [B,3,H,W] in [0,1] or None, latents, info)."""
+    def expand_batch(self, batch, image_i: int = 0, decode: bool = True, as_uint8: bool = False):
+        """generate_data.py:1145-1227 for one batch -> (images [B,3,H,W] in [0,1] or None, latents, info).
+        as_uint8: return the [B,H,W,3] bytes save_image would write (K9) instead of the float image."""
         a = self.args
         dev, wd = self.device, self.weight_dtype
         prompt_embeds = batch["input_ids"].to(dev, dtype=wd, non_blocking=True)
@@ -132,7 +133,10 @@ class Expander:
         if decode:
             with torch.no_grad():                                                          # :1221-1227
                 image = self.vae.decode(latents / self.vae.config.scaling_factor, return_dict=False, generator=generator)[0]
-                image = self.image_processor.postprocess(image, output_type="pt", do_denormalize=[True] * image.shape[0])
+                if as_uint8:   # K9: denormalise + save_image's quantisation in one launch -> [B,H,W,C] bytes (:1227 + :1234)
+                    image = ops.image_to_uint8(image, denormalize=True)
+                else:
+                    image = self.image_processor.postprocess(image, output_type="pt", do_denormalize=[True] * image.shape[0])
         return image, latents, info
 
 
@@ -142,23 +146,82 @@ def output_path(args, batch, i, image_i) -> str:
     return f'{args.output_dir}/{batch["class_names"][i]}/{image_file_path}_expand_{image_i}.png'
 
 
+class AsyncPngWriter:
+    """Device->host copy and PNG encoding off the sampling thread.
+
+    generate_data.py:1230-1234 converts, copies and PNG-encodes every image synchronously before the next batch
+    starts.  Here the [B,H,W,C] bytes from K9 are copied into pinned memory asynchronously; worker threads wait on
+    the copy's event, encode with PIL's default PNG settings (what torchvision.utils.save_image uses, so the files
+    are byte-identical) and publish each file with an atomic rename -- an interrupted run never leaves a truncated
+    PNG that the skip-if-exists resume (:1132-1143) would keep.  At most ``depth`` batches are in flight."""
+
+    def __init__(self, workers: int = 4, depth: int = 4):
+        import collections
+        import concurrent.futures as cf
+        self._pool = cf.ThreadPoolExecutor(max_workers=workers, thread_name_prefix="dd-png")
+        self._pending = collections.deque()
+        self._depth = depth
+
+    @staticmethod
+    def _encode(arr, path):
+        from PIL import Image
+        os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
+        tmp = f"{path}.tmp.{os.getpid()}"
+        Image.fromarray(arr[:, :, 0] if arr.shape[2] == 1 else arr).save(tmp, format="PNG")
+        os.replace(tmp, path)
+
+    def _write(self, host, event, keep, paths):
+        if event is not None:
+            event.synchronize()
+        del keep
+        arr = host.numpy()
+        for i, p in enumerate(paths):
+            self._encode(arr[i], p)
+        return len(paths)
+
+    def submit(self, images_u8: torch.Tensor, paths) -> None:
+        """images_u8: [B,H,W,C] uint8 (CUDA or CPU); paths: B output files."""
+        if images_u8.dtype != torch.uint8 or images_u8.dim() != 4 or images_u8.shape[0] != len(paths):
+            raise ValueError("AsyncPngWriter.submit expects uint8 [B,H,W,C] and one path per image")
+        if images_u8.is_cuda:
+            host = torch.empty(images_u8.shape, dtype=torch.uint8, pin_memory=True)
+            host.copy_(images_u8, non_blocking=True)
+            event = torch.cuda.Event()
+            event.record()
+        else:
+            host, event = images_u8.contiguous(), None
+        self._pending.append(self._pool.submit(self._write, host, event, images_u8, list(paths)))
+        while len(self._pending) > self._depth:
+            self._pending.popleft().result()
+
+    def close(self) -> None:
+        while self._pending:
+            self._pending.popleft().result()
+        self._pool.shutdown(wait=True)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+
+
 def run_expansion(args, expander: Expander, train_dataloader, save: bool = True):
     """generate_data.py:1130-1236: batches x image_i with skip-if-exists resume."""
-    from torchvision.utils import save_image
     n_done = 0
-    for _step, batch in enumerate(train_dataloader):
-        for image_i in range(args.first_image_index, args.num_images_per_prompt):
-            paths = [output_path(args, batch, i, image_i) for i in range(len(batch["image_paths"]))]
-            if save and all(os.path.exists(p) for p in paths):                             # :1132-1143
-                for p in paths:
-                    print(f"File {p} exists, so skipped.")
-                continue
-            image, _lat, info = expander.expand_batch(batch, image_i)
-            for s, t in zip(info["scores"], info["guide_timesteps"]):
-                logger.info("%s in %s step for %s steps period, score: %.4f", args.guidance_type, t, args.guidance_period, float(s))
-            if save:
-                for i, p in enumerate(paths):
-                    os.makedirs(os.path.dirname(p), exist_ok=True)
-                    save_image([image[i]], p)
-            n_done += len(paths)
+    with AsyncPngWriter() as writer:
+        for _step, batch in enumerate(train_dataloader):
+            for image_i in range(args.first_image_index, args.num_images_per_prompt):
+                paths = [output_path(args, batch, i, image_i) for i in range(len(batch["image_paths"]))]
+                if save and all(os.path.exists(p) for p in paths):                             # :1132-1143
+                    for p in paths:
+                        print(f"File {p} exists, so skipped.")
+                    continue
+                image, _lat, info = expander.expand_batch(batch, image_i, as_uint8=save)
+                for s, t in zip(info["scores"], info["guide_timesteps"]):
+                    logger.info("%s in %s step for %s steps period, score: %.4f", args.guidance_type, t, args.guidance_period, float(s))
+                if save:
+                    writer.submit(image, paths)                                                # :1230-1234
+                n_done += len(paths)
     return n_done

@@ -7,7 +7,7 @@ every timed launch by READING a 512 MB buffer (a write-flush would leave dirty l
 bandwidth from the timed kernel), CUDA events on the launching stream, median of ``iters``.
 
 Algorithmic bytes per launch:
-  K5 fwd/bwd 5*B*16384*s   K6 2*B*16384*s   K7 3*B*16384*s   K4 B*(K+3)*D*4   K1 2*N*D*4+N*8   K3 N*D*4+2*N*4   K8 (B*3*512*512 + B*3*224*224)*s
+  K5 fwd/bwd 5*B*16384*s   K6 2*B*16384*s   K7 3*B*16384*s   K4 B*(K+3)*D*4   K1 2*N*D*4+N*8   K3 N*D*4+2*N*4   K8 (B*3*512*512 + B*3*224*224)*s   K9 B*3*512*512*(s+1)
 """
 from __future__ import annotations
 
@@ -130,6 +130,18 @@ def run(want=lambda name: True, iters=10, ks=(3, 5, 10), latent_dtypes=(torch.fl
                     report(f"aten_bicubic_bwd_{dn}_B{B}", nb, timeit(lambda: torch.autograd.grad(yo, xi, gr, retain_graph=True), iters))
                     del xi, yo
                 del img, gr
+    if want("K9"):
+        for dt in latent_dtypes:
+            es = torch.empty(0, dtype=dt).element_size()
+            dn = str(dt).split(".")[-1]
+            for B in (4, 256):
+                img = (torch.randn(B, 3, 512, 512, device=dev) * 0.8).to(dt)
+                u8 = torch.empty(B, 512, 512, 3, dtype=torch.uint8, device=dev)
+                report(f"K9_image_to_uint8_{dn}_B{B}", img.numel() * (es + 1), timeit(lambda: ops.image_to_uint8(img, True, u8), iters))
+                if B == 256:   # the eager sequence it replaces (postprocess denormalize + save_image's quantisation, per batch)
+                    report(f"eager_image_to_uint8_{dn}_B{B}", img.numel() * (es + 1),
+                           timeit(lambda: (img / 2 + 0.5).clamp(0, 1).mul(255).add_(0.5).clamp_(0, 255).permute(0, 2, 3, 1).to(torch.uint8).contiguous(), iters))
+                del img, u8
     N = n_feat
     if want("K1") or want("K3"):
         feat = torch.randn(N, D, device=dev)

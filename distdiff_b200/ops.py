@@ -240,6 +240,25 @@ class BicubicResize(torch.autograd.Function):
 
 
 # ------------------------------------------------------------------------------------------------
+# K9  decoded image -> uint8 HWC (what the PNG encoder reads)
+# ------------------------------------------------------------------------------------------------
+def image_to_uint8(image: torch.Tensor, denormalize: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """[B,C,H,W] decoder output -> [B,H,W,C] uint8, bit-identical to postprocess(do_denormalize) + save_image's
+    mul(255).add_(0.5).clamp_(0,255).permute(1,2,0).to(uint8) in the image's dtype (generate_data.py:1227,1234)."""
+    x = _req(image, "image")
+    if x.dim() != 4:
+        raise DistDiffError(f"image_to_uint8 expects [B,C,H,W], got {tuple(x.shape)}")
+    B, Cc, H, W = x.shape
+    if out is None:
+        out = torch.empty((B, H, W, Cc), dtype=torch.uint8, device=x.device)
+    elif out.shape != (B, H, W, Cc) or out.dtype != torch.uint8 or not out.is_cuda or not out.is_contiguous():
+        raise DistDiffError("image_to_uint8: out must be a contiguous CUDA uint8 [B,H,W,C] tensor")
+    _call("dd_image_to_uint8", x.numel() * (x.element_size() + 1), 1,
+          _ptr(x), B, Cc, H, W, _code(x), int(bool(denormalize)), _ptr(out), _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 # K7  add_noise
 # ------------------------------------------------------------------------------------------------
 def add_noise(x: torch.Tensor, noise: torch.Tensor, a_t: float) -> torch.Tensor:

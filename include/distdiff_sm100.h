@@ -91,6 +91,15 @@ int dd_bicubic_resize_fwd(const void* in, int64_t planes, int Hin, int Win, int 
 int dd_bicubic_resize_bwd(const void* grad_out, int64_t planes, int Hin, int Win, int Hout, int Wout, int dtype,
                           void* grad_in, dd_stream_t stream);
 
+/* ---- K9: final decode -> uint8 HWC for the PNG writer ---------------------------------
+ * Replaces generate_data.py:1227 (VaeImageProcessor.postprocess(do_denormalize=True): (x/2+0.5).clamp(0,1)) and
+ * torchvision.utils.save_image's quantisation at :1234 (mul(255).add_(0.5).clamp_(0,255).permute(1,2,0).to(uint8)).
+ * img: [B,C,H,W] (C = 1, 3 or 4; H*W % 4 == 0), out_hwc: [B,H,W,C] bytes.  Every step is rounded to the storage
+ * type like the eager sequence, so the bytes equal the reference's for f32 / f16 / bf16.  denormalize = 0 skips
+ * the (x/2+0.5).clamp(0,1) part (input already in [0,1]). */
+int dd_image_to_uint8(const void* img, int64_t B, int C, int H, int W, int dtype, int denormalize, uint8_t* out_hwc,
+                      dd_stream_t stream);
+
 /* ---- K4: hierarchical prototype energy, forward + analytic gradient -------------------------------
  * Replaces generate_data.py:707-717 / :747-759 and their autograd backward:
  *     fn    = normalize_f ? f / ||f|| : f                                   (direct mode, :747)

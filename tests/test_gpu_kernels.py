@@ -486,3 +486,38 @@ def test_bicubic_resize_errors(ops, cuda_device):
         ops.bicubic_resize(torch.randn(1, 3, 8, 8), (4, 4))                     # CPU tensor: no fallback
     with pytest.raises(DistDiffError):
         ops.bicubic_resize(torch.randn(1, 1, 512, 512, device=cuda_device), (16, 16))      # 32x down-scaling: region > smem
+
+
+# ------------------------------------------------------------------------------------------- K9 image -> uint8
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(2, 3, 64, 64), (1, 1, 6, 6), (1, 4, 10, 14), (1, 3, 512, 512)])
+@pytest.mark.parametrize("denorm", [True, False])
+def test_image_to_uint8_bitexact(ops, cuda_device, dtype, shape, denorm):
+    from oracle import image as o_img
+    x = torch.randn(shape, generator=_g(21)) * (0.9 if denorm else 0.4) + (0.0 if denorm else 0.5)
+    flat = x.view(-1)
+    # exact half-way and boundary values of the quantiser
+    special = torch.tensor([-1.0, 1.0, 0.0, -1.5, 1.5, 1 / 255, 0.5 / 255, 127.5 / 255, 254.5 / 255, 2 * 0.5 / 255 - 1, 2 * 100.5 / 255 - 1])
+    flat[:special.numel()] = special
+    x = x.to(dtype)
+    got = ops.image_to_uint8(x.to(cuda_device), denormalize=denorm).cpu().numpy()
+    ref = o_img.decode_to_uint8(x, do_denormalize=denorm)       # the reference's eager ops in the image dtype, on the CPU
+    assert got.shape == ref.shape and got.dtype == np.uint8
+    assert np.array_equal(got, ref)
+
+
+def test_png_writer_matches_save_image(ops, cuda_device, tmp_path):
+    from torchvision.utils import save_image
+    from distdiff_b200.expand import AsyncPngWriter
+    from oracle import image as o_img
+    x = (torch.randn((3, 3, 64, 48), generator=_g(22)) * 0.8).half()
+    ref_paths = [str(tmp_path / f"ref_{i}.png") for i in range(3)]
+    img = o_img.denormalize(x)                                   # generate_data.py:1227
+    for i, p in enumerate(ref_paths):
+        save_image([img[i]], p)                                  # generate_data.py:1234
+    ours = [str(tmp_path / "cls" / f"ours_{i}.png") for i in range(3)]
+    with AsyncPngWriter(workers=2, depth=1) as w:
+        w.submit(ops.image_to_uint8(x.to(cuda_device)), ours)
+    for a, b in zip(ref_paths, ours):
+        assert open(a, "rb").read() == open(b, "rb").read()      # byte-identical files
+    assert not [f for f in (tmp_path / "cls").iterdir() if ".tmp." in f.name]

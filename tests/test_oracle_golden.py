@@ -203,3 +203,31 @@ def test_bicubic_axis_matrix_properties():
     assert (np.count_nonzero(M, axis=1) <= 4).all()         # 4 taps per output
     assert (np.count_nonzero(M, axis=0) <= 3).all()         # <= 2-3 outputs touch one input at scale 2.29
     assert np.array_equal(resize.axis_matrix(17, 17), np.eye(17, dtype=np.float32))
+
+
+# ------------------------------------------------------------------------------------------- image -> PNG (K9 oracle, writer)
+def test_png_writer_cpu_bytes_and_atomicity(tmp_path):
+    """AsyncPngWriter (host logic, no GPU) writes exactly PIL's default PNG of the oracle's uint8 array."""
+    from distdiff_b200.expand import AsyncPngWriter
+    from oracle import image as o_img
+    x = torch.randn((2, 3, 16, 20), generator=torch.Generator().manual_seed(5)) * 0.8
+    u8 = o_img.decode_to_uint8(x)
+    paths = [str(tmp_path / "a" / "b" / f"img_{i}.png") for i in range(2)]
+    with AsyncPngWriter(workers=2, depth=1) as w:
+        w.submit(torch.from_numpy(u8), paths)
+    for i, p in enumerate(paths):
+        assert open(p, "rb").read() == o_img.png_bytes(u8[i])
+    assert sorted(f.name for f in (tmp_path / "a" / "b").iterdir()) == ["img_0.png", "img_1.png"]
+    with pytest.raises(ValueError):
+        AsyncPngWriter().submit(torch.zeros(2, 3, 4, 4), paths)
+
+
+def test_decode_to_uint8_matches_save_image_array():
+    from torchvision.utils import save_image
+    from oracle import image as o_img
+    import io
+    from PIL import Image
+    x = (torch.randn((1, 3, 8, 12), generator=torch.Generator().manual_seed(6)) * 0.8)
+    buf = io.BytesIO()
+    save_image([o_img.denormalize(x)[0]], buf, format="png")
+    assert np.array_equal(np.asarray(Image.open(io.BytesIO(buf.getvalue()))), o_img.decode_to_uint8(x)[0])

@@ -36,7 +36,7 @@ def parse():
     p.add_argument("--steps", type=int, default=3)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    p.add_argument("--batch", type=int, default=4, help="images per step and GPU (train_batch_size)")
+    p.add_argument("--batch", type=int, default=8, help="images per step and GPU (train_batch_size)")
     p.add_argument("--dtype", default="fp16", choices=["fp16", "bf16", "fp32"], help="UNet/VAE/latent storage type (reference: fp16)")
     p.add_argument("--no-cuda-graph", action="store_true")
     p.add_argument("--no-channels-last", action="store_true", help="keep UNet/VAE/guide in NCHW (PyTorch-side layout choice)")

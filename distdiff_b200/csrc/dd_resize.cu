@@ -9,12 +9,23 @@
 // then along y, all in fp32; the result is rounded once to the storage type.
 //
 // Forward: one CTA per 32x32 output tile of one (b, c) plane.  The input region of the tile (~77x77 for 512->224)
-// is staged in shared memory as fp32 with 16-byte global loads, then every thread produces 4 outputs from 16
-// shared-memory taps each -> every input element is read from HBM ~1.1 times (tile halo), L2 absorbs the rest.
-// Backward: GATHER form, one CTA per 64x32 input tile: the upstream-gradient region is staged in shared memory,
-// a horizontal pass builds tmp[oy][ix] = sum_ox g[oy][ox] * wx(ox, ix), a vertical pass sums
-// tmp[oy][ix] * wy(oy, iy) -- a fixed summation order, no atomics, bit-reproducible.
+// is staged in shared memory as fp32 with 16-byte global loads (every input element is read from HBM ~1.1 times,
+// tile halo; L2 absorbs the rest), then two passes that follow ATen's x-then-y order exactly:
+//   pass 1  tmpT[ox][ry] = cubic_interp1d along x of staged row ry   (lanes run along ry: the row stride is ODD, so the
+//           4 taps of a warp hit 32 different banks -- with lanes along ox the stride-2.29 tap addresses of a
+//           512->224 resize are 2-3-way bank conflicts, which is what bounded the first version of this kernel)
+//   pass 2  out[oy][ox]  = cubic_interp1d along y of tmpT[ox][.]     (lanes along ox, odd stride again)
+// Each x-interpolated row is computed once per tile instead of once per output row that uses it (77 vs 128 per column).
+// Backward: GATHER form, one CTA per 64 x `by` input tile (by = 128 rows for 512->224): the upstream-gradient region
+// is staged in shared memory, a horizontal pass builds tmp[oy][ix] = sum_ox g[oy][ox] * wx(ox, ix), a vertical pass
+// sums tmp[oy][ix] * wy(oy, iy) -- a fixed summation order, no atomics, bit-reproducible.  The fast path keeps the
+// exact candidate list of every input index (first touching output + MC <= 4 weights, MC = 2 for 512->224) in one
+// float4 per index; the generic path (strong up-scaling, MC > 4) walks a conservative candidate range.
 #include "dd_common.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <vector>
 
 namespace dd {
 
@@ -29,9 +40,12 @@ struct Taps {
 };
 
 // ATen: area_pixel_compute_source_index(scale, dst, align_corners=false, cubic=true) + get_cubic_upsample_coefficients
+__device__ __forceinline__ float src_coord(int o, float scale) { return scale * (o + 0.5f) - 0.5f; }
+__device__ __forceinline__ int tap_floor(int o, float scale) { return (int)floorf(src_coord(o, scale)); }   // == cubic_taps(o).f
+
 __device__ __forceinline__ Taps cubic_taps(int o, float scale) {
     const float A = -0.75f;
-    const float real = scale * (o + 0.5f) - 0.5f;
+    const float real = src_coord(o, scale);
     const float fl = floorf(real);
     const float t = real - fl;
     Taps r;
@@ -50,70 +64,214 @@ __device__ __forceinline__ Taps cubic_taps(int o, float scale) {
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 // -------------------------------------------------------------------------------------------------- forward
+// The staged region covers the tile's taps in VIRTUAL coordinates (f-1 .. f+2 before clamping): out-of-image rows and
+// columns are filled with the clamped pixel while staging, so the 4 taps of every output are 4 CONSECUTIVE staged
+// elements and the inner loops need one address per output instead of four.
 template <typename T>
 __global__ void __launch_bounds__(RS_THREADS)
 bicubic_fwd_kernel(const T* __restrict__ in, T* __restrict__ out, int Hin, int Win, int Hout, int Wout, float sy, float sx,
-                   int tiles_x, int tiles_y, int rw_pad, int rh_max, int vec_ok) {
-    extern __shared__ __align__(16) float region[];   // [rh_max][rw_pad] staged input, then the per-row tap table
-    constexpr int VN = Vec16<T>::N;
-    float* ty_c = region + (size_t)rh_max * rw_pad;                    // [RS_TO][4]
-    int* ty_r = reinterpret_cast<int*>(ty_c + RS_TO * 4);              // [RS_TO][4] staged row of each tap
-    const int tile = blockIdx.x % (tiles_x * tiles_y);
-    const int64_t plane = blockIdx.x / (tiles_x * tiles_y);
-    const int ox0 = (tile % tiles_x) * RS_TO, oy0 = (tile / tiles_x) * RS_TO;
-    const int ox1 = min(ox0 + RS_TO, Wout), oy1 = min(oy0 + RS_TO, Hout);
-    // input region touched by the tile (source coordinates are monotone in the output index)
-    const int x_lo = clampi(cubic_taps(ox0, sx).f - 1, 0, Win - 1), x_hi = clampi(cubic_taps(ox1 - 1, sx).f + 2, 0, Win - 1);
-    const int y_lo = clampi(cubic_taps(oy0, sy).f - 1, 0, Hin - 1), y_hi = clampi(cubic_taps(oy1 - 1, sy).f + 2, 0, Hin - 1);
-    const int xa = vec_ok ? (x_lo / VN) * VN : x_lo;   // 16-byte aligned start of the staged rows
-    const int rh = y_hi - y_lo + 1;
+                   int tiles_x, int tiles_y, int rw_pad, int rh_max, int tp) {
+    extern __shared__ __align__(16) float sm[];
+    float4* tx_c = reinterpret_cast<float4*>(sm);                      // [RS_TO] x-tap weights of the tile's columns
+    float4* ty_c = tx_c + RS_TO;                                       // [RS_TO] y-tap weights of the tile's rows
+    int* tx_0 = reinterpret_cast<int*>(ty_c + RS_TO);                  // [RS_TO] staged column of the first tap
+    int* ty_0 = tx_0 + RS_TO;                                          // [RS_TO] staged row of the first tap
+    float* region = reinterpret_cast<float*>(ty_0 + RS_TO);            // [rh_max][rw_pad] staged input, rw_pad odd
+    float* tmpT = region + (size_t)rh_max * rw_pad;                    // [RS_TO][tp]      x-interpolated rows, tp odd
+    const int tiles = tiles_x * tiles_y;
+    const int64_t plane = blockIdx.x / tiles;
+    const int tile = blockIdx.x - (int)plane * tiles;
+    const int tyi = tile / tiles_x;
+    const int ox0 = (tile - tyi * tiles_x) * RS_TO, oy0 = tyi * RS_TO;
+    const int nx = min(RS_TO, Wout - ox0), ny = min(RS_TO, Hout - oy0);
+    const int vx_lo = tap_floor(ox0, sx) - 1, vy_lo = tap_floor(oy0, sy) - 1;
+    const int rw = tap_floor(ox0 + nx - 1, sx) + 2 - vx_lo + 1, rh = tap_floor(oy0 + ny - 1, sy) + 2 - vy_lo + 1;
     const T* src = in + plane * (int64_t)Hin * Win;
-    if (threadIdx.x < RS_TO && oy0 + (int)threadIdx.x < oy1) {         // vertical taps of the tile's rows, once per CTA
-        const Taps t = cubic_taps(oy0 + threadIdx.x, sy);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            ty_c[threadIdx.x * 4 + k] = t.c[k];
-            ty_r[threadIdx.x * 4 + k] = (clampi(t.f - 1 + k, 0, Hin - 1) - y_lo) * rw_pad;
-        }
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // stage: one warp per row, lanes along x (coalesced), borders replicated
+    for (int ry = warp; ry < rh; ry += RS_THREADS / 32) {
+        const T* srow = src + (int64_t)clampi(vy_lo + ry, 0, Hin - 1) * Win;
+        float* drow = region + ry * rw_pad;
+        for (int rx = lane; rx < rw; rx += 32) drow[rx] = to_f32<T>(srow[clampi(vx_lo + rx, 0, Win - 1)]);
     }
-    if (vec_ok) {
-        const int nv = (x_hi - xa) / VN + 1;
-        for (int i = threadIdx.x; i < rh * nv; i += RS_THREADS) {
-            const int ry = i / nv, v = i - ry * nv;
-            Vec16<T> ld;
-            ld.load(src + (int64_t)(y_lo + ry) * Win + xa + v * VN);
-            float* dst = region + ry * rw_pad + v * VN;
-#pragma unroll
-            for (int j = 0; j < VN; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(ld.v[j], ld.v[j + 1], ld.v[j + 2], ld.v[j + 3]);
+    if (tid < RS_TO) {                                                 // tap tables of the tile, once per CTA
+        if (tid < ny) {
+            const Taps t = cubic_taps(oy0 + tid, sy);
+            ty_c[tid] = make_float4(t.c[0], t.c[1], t.c[2], t.c[3]);
+            ty_0[tid] = t.f - 1 - vy_lo;
         }
-    } else {
-        const int rw = x_hi - xa + 1;
-        for (int i = threadIdx.x; i < rh * rw; i += RS_THREADS) {
-            const int ry = i / rw, rx = i - ry * rw;
-            region[ry * rw_pad + rx] = to_f32<T>(src[(int64_t)(y_lo + ry) * Win + xa + rx]);
+    } else if (tid < 2 * RS_TO) {
+        const int l = tid - RS_TO;
+        if (l < nx) {
+            const Taps t = cubic_taps(ox0 + l, sx);
+            tx_c[l] = make_float4(t.c[0], t.c[1], t.c[2], t.c[3]);
+            tx_0[l] = t.f - 1 - vx_lo;
         }
     }
     __syncthreads();
-    const int lx = threadIdx.x % RS_TO;
-    const int ox = ox0 + lx;
-    if (ox >= ox1) return;
-    const Taps tx = cubic_taps(ox, sx);
-    int cx[4];
+    {   // pass 1: cubic_interp1d along x of every staged row (lanes along rows, odd row stride: conflict-free)
+        constexpr int PW = RS_TO / (RS_THREADS / 32);                  // columns per warp
+        float4 c[PW];
+        int x0[PW];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) cx[k] = clampi(tx.f - 1 + k, 0, Win - 1) - xa;
-    T* dst = out + plane * (int64_t)Hout * Wout;
-    for (int ly = threadIdx.x / RS_TO; oy0 + ly < oy1; ly += RS_THREADS / RS_TO) {
-        const float4 cy = *reinterpret_cast<const float4*>(ty_c + ly * 4);
-        const int4 ro = *reinterpret_cast<const int4*>(ty_r + ly * 4);
-        const int roff[4] = {ro.x, ro.y, ro.z, ro.w};
-        float rowv[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float* r = region + roff[i];
-            rowv[i] = r[cx[0]] * tx.c[0] + r[cx[1]] * tx.c[1] + r[cx[2]] * tx.c[2] + r[cx[3]] * tx.c[3];   // cubic_interp1d along x
+        for (int j = 0; j < PW; ++j) {
+            const int l = min(warp + j * (RS_THREADS / 32), nx - 1);
+            c[j] = tx_c[l]; x0[j] = tx_0[l];
         }
-        const float v = rowv[0] * cy.x + rowv[1] * cy.y + rowv[2] * cy.z + rowv[3] * cy.w;               // then along y
-        dst[(int64_t)(oy0 + ly) * Wout + ox] = from_f32<T>(v);
+        for (int ry = lane; ry < rh; ry += 32) {
+            const float* rrow = region + ry * rw_pad;
+#pragma unroll
+            for (int j = 0; j < PW; ++j) {
+                const int l = warp + j * (RS_THREADS / 32);
+                const float* r = rrow + x0[j];
+                const float v = r[0] * c[j].x + r[1] * c[j].y + r[2] * c[j].z + r[3] * c[j].w;
+                if (l < nx) tmpT[l * tp + ry] = v;
+            }
+        }
+    }
+    __syncthreads();
+    // pass 2: then along y (lanes along x, odd column stride)
+    if (lane >= nx) return;
+    T* dst = out + plane * (int64_t)Hout * Wout + (int64_t)oy0 * Wout + ox0 + lane;
+    const float* tcol = tmpT + lane * tp;
+    for (int ly = warp; ly < ny; ly += RS_THREADS / 32) {
+        const float4 cy = ty_c[ly];
+        const float* t = tcol + ty_0[ly];
+        const float v = t[0] * cy.x + t[1] * cy.y + t[2] * cy.z + t[3] * cy.w;
+        dst[(int64_t)ly * Wout] = from_f32<T>(v);
+    }
+}
+
+// Vectorised variant (Win % VN == 0, 16-byte aligned input): rows are staged with 16-byte loads / stores into a
+// region whose row stride is 4 * odd floats, so that 8 consecutive rows cover all 32 banks with 16-byte accesses.
+// Pass 1 (lanes along rows) reads the 4 taps as two aligned float4 and picks them with a WARP-UNIFORM shift
+// (all lanes of a warp work on the same output column), i.e. 2 conflict-free LDS.128 per (row, column).
+__device__ __forceinline__ float4 lds128(const float* p) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+    return v;
+}
+__device__ __forceinline__ int floor_div(int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
+
+template <typename T>
+__global__ void __launch_bounds__(RS_THREADS)
+bicubic_fwd_vec_kernel(const T* __restrict__ in, T* __restrict__ out, int Hin, int Win, int Hout, int Wout, float sy, float sx,
+                       int tiles_x, int tiles_y, int S, int rh_max, int tp) {
+    extern __shared__ __align__(16) float sm[];
+    constexpr int VN = Vec16<T>::N;
+    float4* tx_c = reinterpret_cast<float4*>(sm);                      // [RS_TO] x-tap weights of the tile's columns
+    float4* ty_c = tx_c + RS_TO;                                       // [RS_TO] y-tap weights of the tile's rows
+    int* tx_0 = reinterpret_cast<int*>(ty_c + RS_TO);                  // [RS_TO] staged column of the first tap
+    int* ty_0 = tx_0 + RS_TO;                                          // [RS_TO] staged row of the first tap
+    float* region = reinterpret_cast<float*>(ty_0 + RS_TO);            // [rh_max][S] staged input, S = 4 * odd
+    float* tmpT = region + (size_t)rh_max * S;                         // [RS_TO][tp]  x-interpolated rows, tp odd
+    const int tiles = tiles_x * tiles_y;
+    const int64_t plane = blockIdx.x / tiles;
+    const int tile = blockIdx.x - (int)plane * tiles;
+    const int tyi = tile / tiles_x;
+    const int ox0 = (tile - tyi * tiles_x) * RS_TO, oy0 = tyi * RS_TO;
+    const int nx = min(RS_TO, Wout - ox0), ny = min(RS_TO, Hout - oy0);
+    const int vx_lo = tap_floor(ox0, sx) - 1, vy_lo = tap_floor(oy0, sy) - 1;
+    const int vx_hi = tap_floor(ox0 + nx - 1, sx) + 2, rh = tap_floor(oy0 + ny - 1, sy) + 2 - vy_lo + 1;
+    const int xa = floor_div(vx_lo, VN) * VN;                          // staged column 0 <-> image column xa (may be < 0)
+    const int nv = (vx_hi - xa) / VN + 1;                              // 16-byte vectors per staged row
+    const T* src = in + plane * (int64_t)Hin * Win;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    {   // all loads of a round are issued before the first store: one HBM round trip per <= 8 vectors of a thread
+        constexpr int UN = sizeof(T) == 4 ? 8 : 4;   // 16-bit rows have half as many vectors
+        const float inv_nv = 1.0f / (float)nv;
+        const int total = rh * nv;
+        for (int i0 = tid; i0 < total; i0 += UN * RS_THREADS) {
+            Vec16<T> ld[UN];
+            int off[UN];
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                const int i = i0 + u * RS_THREADS;
+                off[u] = -1;
+                if (i < total) {
+                    const int ry = (int)(((float)i + 0.5f) * inv_nv);     // i / nv (exact: i < 2^16, error << 0.5 / nv)
+                    const int col = xa + (i - ry * nv) * VN;
+                    if (col >= 0 && col < Win) {                           // vectors are entirely inside or outside the image
+                        ld[u].load(src + (int64_t)clampi(vy_lo + ry, 0, Hin - 1) * Win + col);
+                        off[u] = ry * S + (col - xa);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                if (off[u] >= 0) {
+                    float* dst = region + off[u];
+#pragma unroll
+                    for (int j = 0; j < VN; j += 4)
+                        *reinterpret_cast<float4*>(dst + j) = make_float4(ld[u].v[j], ld[u].v[j + 1], ld[u].v[j + 2], ld[u].v[j + 3]);
+                }
+            }
+        }
+    }
+    if (vx_lo < 0 || vx_hi >= Win) {                                   // replicated border columns (edge tiles only)
+        for (int ry = tid; ry < rh; ry += RS_THREADS) {
+            const T* srow = src + (int64_t)clampi(vy_lo + ry, 0, Hin - 1) * Win;
+            float* drow = region + ry * S - xa;
+            if (vx_lo < 0) {
+                const float e = to_f32<T>(srow[0]);
+                for (int vx = vx_lo; vx < 0; ++vx) drow[vx] = e;
+            }
+            if (vx_hi >= Win) {
+                const float e = to_f32<T>(srow[Win - 1]);
+                for (int vx = Win; vx <= vx_hi; ++vx) drow[vx] = e;
+            }
+        }
+    }
+    if (tid < RS_TO) {                                                 // tap tables of the tile, once per CTA
+        if (tid < ny) {
+            const Taps t = cubic_taps(oy0 + tid, sy);
+            ty_c[tid] = make_float4(t.c[0], t.c[1], t.c[2], t.c[3]);
+            ty_0[tid] = t.f - 1 - vy_lo;
+        }
+    } else if (tid < 2 * RS_TO) {
+        const int l = tid - RS_TO;
+        if (l < nx) {
+            const Taps t = cubic_taps(ox0 + l, sx);
+            tx_c[l] = make_float4(t.c[0], t.c[1], t.c[2], t.c[3]);
+            tx_0[l] = t.f - 1 - xa;
+        }
+    }
+    __syncthreads();
+    {   // pass 1: cubic_interp1d along x of every staged row
+        constexpr int PW = RS_TO / (RS_THREADS / 32);                  // columns per warp
+#pragma unroll
+        for (int j = 0; j < PW; ++j) {
+            const int l = warp + j * (RS_THREADS / 32);
+            if (l >= nx) break;
+            const float4 c = tx_c[l];
+            const int x0 = tx_0[l];
+            const int sh = x0 & 3;                                     // warp-uniform
+            const float* rcol = region + (x0 & ~3);
+            float* trow = tmpT + l * tp;
+            for (int ry = lane; ry < rh; ry += 32) {
+                const float4 lo = lds128(rcol + ry * S);               // forced 16-byte loads: with S = 4 * odd they are
+                const float4 hi = lds128(rcol + ry * S + 4);           // conflict-free, the 8-byte pieces ptxas prefers are not
+                float v;
+                switch (sh) {
+                    case 0: v = lo.x * c.x + lo.y * c.y + lo.z * c.z + lo.w * c.w; break;
+                    case 1: v = lo.y * c.x + lo.z * c.y + lo.w * c.z + hi.x * c.w; break;
+                    case 2: v = lo.z * c.x + lo.w * c.y + hi.x * c.z + hi.y * c.w; break;
+                    default: v = lo.w * c.x + hi.x * c.y + hi.y * c.z + hi.z * c.w; break;
+                }
+                trow[ry] = v;
+            }
+        }
+    }
+    __syncthreads();
+    // pass 2: then along y (lanes along x, odd column stride)
+    if (lane >= nx) return;
+    T* dst = out + plane * (int64_t)Hout * Wout + (int64_t)oy0 * Wout + ox0 + lane;
+    const float* tcol = tmpT + lane * tp;
+    for (int ly = warp; ly < ny; ly += RS_THREADS / 32) {
+        const float4 cy = ty_c[ly];
+        const float* t = tcol + ty_0[ly];
+        const float v = t[0] * cy.x + t[1] * cy.y + t[2] * cy.z + t[3] * cy.w;
+        dst[(int64_t)ly * Wout] = from_f32<T>(v);
     }
 }
 
@@ -198,6 +356,217 @@ bicubic_bwd_kernel(const T* __restrict__ gout, T* __restrict__ gin, int Hin, int
     }
 }
 
+// ---- fast path: exact candidate lists, MC <= 4 weights per input index --------------------------------------------
+// does output o (tap base f) touch input index i?  taps f-1..f+2 clamped to [0, n-1]
+__device__ __forceinline__ bool touches(int f, int i, int n) {
+    return clampi(f - 1, 0, n - 1) == i || clampi(f, 0, n - 1) == i || clampi(f + 1, 0, n - 1) == i || clampi(f + 2, 0, n - 1) == i;
+}
+// the sum of the tap weights of an output (base f, weights c) whose clamped position is i -- tap_weight() from a table
+__device__ __forceinline__ float tap_weight_tab(int f, const float4& c, int i, int n) {
+    float w = 0.f;
+    if (clampi(f - 1, 0, n - 1) == i) w += c.x;
+    if (clampi(f, 0, n - 1) == i) w += c.y;
+    if (clampi(f + 1, 0, n - 1) == i) w += c.z;
+    if (clampi(f + 2, 0, n - 1) == i) w += c.w;
+    return w;
+}
+// candidate list of input index i along one axis: first touching output (relative to the staged range [o_lo, o_lo+n_st))
+// and the weights of the next MC outputs (0 past the last touching one).  of/oc: tap tables of the staged outputs.
+template <int MC>
+__device__ __forceinline__ void candidates(int i, bool valid, float scale, int n_in, int n_out, int o_lo, int n_st,
+                                           const int* __restrict__ of, const float4* __restrict__ oc, float4& w, int& first) {
+    float wv[4] = {0.f, 0.f, 0.f, 0.f};
+    int j0 = n_st;
+    if (valid) {
+        int lo, hi;
+        out_range(i, scale, n_out, lo, hi);
+        j0 = lo - o_lo;
+        if (j0 < 0) j0 = 0;
+        while (j0 < n_st && !touches(of[j0], i, n_in)) ++j0;
+#pragma unroll
+        for (int m = 0; m < MC; ++m)
+            if (j0 + m < n_st) wv[m] = tap_weight_tab(of[j0 + m], oc[j0 + m], i, n_in);
+    }
+    w = make_float4(wv[0], wv[1], wv[2], wv[3]);
+    first = j0;
+}
+
+// 4 consecutive results -> storage type (one 16-byte / 8-byte store when `vec`, else the valid scalars)
+template <typename T>
+__device__ __forceinline__ void store4(T* p, const float (&a)[4], bool vec, int nvalid) {
+    if (vec) {
+        if constexpr (sizeof(T) == 4) {
+            *reinterpret_cast<float4*>(p) = make_float4(a[0], a[1], a[2], a[3]);
+        } else {
+            T h[4] = {from_f32<T>(a[0]), from_f32<T>(a[1]), from_f32<T>(a[2]), from_f32<T>(a[3])};
+            *reinterpret_cast<uint2*>(p) = *reinterpret_cast<const uint2*>(h);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (j < nvalid) p[j] = from_f32<T>(a[j]);
+    }
+}
+
+// smem: oc_x [gw_max] f4 | oc_y [gh_max] f4 | wx [RS_BX] f4 | wy [by] f4 | tmp [gh_max + MC][RS_BX] | gs [gh_max][GW] |
+//       of_x [gw_max] | of_y [gh_max] | lox [RS_BX] | loy [by]          (GW = gw_max + MC: zero columns behind every row)
+// Both passes give every thread 4 adjacent input columns: 16 threads cover a tile row, a warp two rows.
+// VEC (Wout % VN == 0, 16-byte aligned grad_out): the staged region starts at a 16-byte boundary of the row and is
+// filled with 16-byte loads / stores; GW is then a multiple of the vector width.
+template <typename T, int MC, bool VEC>
+__global__ void __launch_bounds__(RS_THREADS)
+bicubic_bwd_fast_kernel(const T* __restrict__ gout, T* __restrict__ gin, int Hin, int Win, int Hout, int Wout, float sy, float sx,
+                        int tiles_x, int tiles_y, int gw_max, int gh_max, int by, int vec_ok, int GW) {
+    extern __shared__ __align__(16) float sm[];
+    constexpr int VN = Vec16<T>::N;
+    float4* oc_x = reinterpret_cast<float4*>(sm);
+    float4* oc_y = oc_x + gw_max;
+    float4* wx = oc_y + gh_max;
+    float4* wy = wx + RS_BX;
+    float* tmp = reinterpret_cast<float*>(wy + by);
+    float* gs = tmp + (size_t)(gh_max + MC) * RS_BX;
+    int* of_x = reinterpret_cast<int*>(gs + (size_t)gh_max * GW);
+    int* of_y = of_x + gw_max;
+    int* lox = of_y + gh_max;
+    int* loy = lox + RS_BX;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tiles = tiles_x * tiles_y;
+    const int64_t plane = blockIdx.x / tiles;
+    const int tile = blockIdx.x - (int)plane * tiles;
+    const int tyi = tile / tiles_x;
+    const int ix0 = (tile - tyi * tiles_x) * RS_BX, iy0 = tyi * by;
+    const int ix1 = min(ix0 + RS_BX, Win), iy1 = min(iy0 + by, Hin);
+    int ox_lo, ox_hi, oy_lo, oy_hi, t0, t1;
+    out_range(ix0, sx, Wout, ox_lo, t1); out_range(ix1 - 1, sx, Wout, t0, ox_hi);
+    out_range(iy0, sy, Hout, oy_lo, t1); out_range(iy1 - 1, sy, Hout, t0, oy_hi);
+    if (VEC) ox_lo = (ox_lo / VN) * VN;
+    const int gw = ox_hi - ox_lo + 1, gh = oy_hi - oy_lo + 1;
+    const T* g = gout + plane * (int64_t)Hout * Wout + (int64_t)oy_lo * Wout + ox_lo;
+    if (VEC) {   // 16-byte vectors; whole vectors past the region / the image row are zeros
+        constexpr int UN = sizeof(T) == 4 ? 4 : 2;
+        const int nvr = GW / VN;
+        const float inv = 1.0f / (float)nvr;
+        const int total = gh * nvr;
+        for (int i0 = tid; i0 < total; i0 += UN * RS_THREADS) {   // all loads of a round before the first store
+            Vec16<T> ld[UN];
+            int off[UN];
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                const int i = i0 + u * RS_THREADS;
+                off[u] = -1;
+#pragma unroll
+                for (int j = 0; j < VN; ++j) ld[u].v[j] = 0.f;
+                if (i < total) {
+                    const int ry = (int)(((float)i + 0.5f) * inv), c0 = (i - ry * nvr) * VN;
+                    off[u] = ry * GW + c0;
+                    if (c0 < gw && ox_lo + c0 < Wout) ld[u].load(g + (int64_t)ry * Wout + c0);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                if (off[u] >= 0) {
+                    float* dst = gs + off[u];
+#pragma unroll
+                    for (int j = 0; j < VN; j += 4)
+                        *reinterpret_cast<float4*>(dst + j) = make_float4(ld[u].v[j], ld[u].v[j + 1], ld[u].v[j + 2], ld[u].v[j + 3]);
+                }
+            }
+        }
+    } else {     // one warp per row, zero columns gw..GW-1
+        for (int ry = warp; ry < gh; ry += RS_THREADS / 32) {
+            const T* grow = g + (int64_t)ry * Wout;
+            float* drow = gs + ry * GW;
+            for (int rx = lane; rx < GW; rx += 32) drow[rx] = rx < gw ? to_f32<T>(grow[rx]) : 0.f;
+        }
+    }
+    for (int i = tid; i < MC * RS_BX; i += RS_THREADS) tmp[gh * RS_BX + i] = 0.f;   // zero rows behind tmp
+    // tap tables of the staged outputs (one cubic_taps per output row / column of the region)
+    for (int j = tid; j < gw + gh; j += RS_THREADS) {
+        const bool isx = j < gw;
+        const int jj = isx ? j : j - gw;
+        const Taps t = cubic_taps((isx ? ox_lo : oy_lo) + jj, isx ? sx : sy);
+        (isx ? of_x : of_y)[jj] = t.f;
+        (isx ? oc_x : oc_y)[jj] = make_float4(t.c[0], t.c[1], t.c[2], t.c[3]);
+    }
+    __syncthreads();
+    // transposed (gather) tables: first touching output + MC weights per input column / row of the tile
+    for (int l = tid; l < RS_BX + by; l += RS_THREADS) {
+        float4 w; int first;
+        if (l < RS_BX) {
+            candidates<MC>(ix0 + l, ix0 + l < ix1, sx, Win, Wout, ox_lo, gw, of_x, oc_x, w, first);
+            wx[l] = w; lox[l] = first;
+        } else {
+            const int r = l - RS_BX;
+            candidates<MC>(iy0 + r, iy0 + r < iy1, sy, Hin, Hout, oy_lo, gh, of_y, oc_y, w, first);
+            wy[r] = w; loy[r] = first * RS_BX;
+        }
+    }
+    __syncthreads();
+    constexpr int QPR = RS_BX / 4;                 // threads per tile row
+    constexpr int RPI = RS_THREADS / QPR;          // rows per iteration
+    const int q = tid % QPR, rgrp = tid / QPR;
+    {   // horizontal pass: tmp[ry][ix] = sum_m gs[ry][lox[ix] + m] * wx[ix][m]
+        float w[4][4];
+        int l0[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const float4 w4 = wx[4 * q + c];
+            w[c][0] = w4.x; w[c][1] = w4.y; w[c][2] = w4.z; w[c][3] = w4.w;
+            l0[c] = lox[4 * q + c];
+        }
+        for (int ry = rgrp; ry < gh; ry += RPI) {
+            const float* gr = gs + ry * GW;
+            float a[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                a[c] = 0.f;
+#pragma unroll
+                for (int m = 0; m < MC; ++m) a[c] += gr[l0[c] + m] * w[c][m];
+            }
+            *reinterpret_cast<float4*>(tmp + ry * RS_BX + 4 * q) = make_float4(a[0], a[1], a[2], a[3]);
+        }
+    }
+    __syncthreads();
+    // vertical pass: gin[iy][ix] = sum_m tmp[loy[iy] + m][ix] * wy[iy][m]
+    const int nvalid = ix1 - (ix0 + 4 * q);
+    if (nvalid <= 0) return;
+    const bool vec = vec_ok && nvalid >= 4;
+    T* dst = gin + plane * (int64_t)Hin * Win + (int64_t)iy0 * Win + ix0 + 4 * q;
+    const int nrow = iy1 - iy0;
+    for (int ly = rgrp; ly < nrow; ly += RPI) {
+        const float4 w4 = wy[ly];
+        const float w[4] = {w4.x, w4.y, w4.z, w4.w};
+        const float* tr = tmp + loy[ly] + 4 * q;
+        float a[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int m = 0; m < MC; ++m) {
+            const float4 t = *reinterpret_cast<const float4*>(tr + m * RS_BX);
+            a[0] += t.x * w[m]; a[1] += t.y * w[m]; a[2] += t.z * w[m]; a[3] += t.w * w[m];
+        }
+        store4<T>(dst + (int64_t)ly * Win, a, vec, nvalid);
+    }
+}
+
+// largest number of outputs that touch one input index along an axis (host, conservative: an output whose source
+// coordinate is within 1e-3 of an integer counts for both neighbours, so device rounding can never exceed it)
+static int max_candidates(int n_in, int n_out) {
+    thread_local int c_in = -1, c_out = -1, c_val = 0;
+    if (n_in == c_in && n_out == c_out) return c_val;
+    const double scale = (double)((float)n_in / (float)n_out);
+    std::vector<int> diff(n_in + 1, 0);
+    for (int o = 0; o < n_out; ++o) {
+        const double real = scale * (o + 0.5) - 0.5;
+        int lo = (int)std::floor(real - 1e-3) - 1, hi = (int)std::floor(real + 1e-3) + 2;
+        lo = lo < 0 ? 0 : (lo > n_in - 1 ? n_in - 1 : lo);
+        hi = hi < 0 ? 0 : (hi > n_in - 1 ? n_in - 1 : hi);
+        diff[lo] += 1; diff[hi + 1] -= 1;
+    }
+    int best = 0, run = 0;
+    for (int i = 0; i < n_in; ++i) { run += diff[i]; best = run > best ? run : best; }
+    c_in = n_in; c_out = n_out; c_val = best;
+    return best;
+}
+
 static int out_span(int n_tile, float scale) { return (int)((n_tile + 4) / scale) + 8; }
 static int cand(float scale) { const int c = (int)(4.f / scale) + 5; return c | 1; }
 
@@ -205,25 +574,77 @@ template <typename T>
 static int launch_fwd(const void* in, void* out, int64_t planes, int Hin, int Win, int Hout, int Wout, cudaStream_t st) {
     const float sy = (float)Hin / (float)Hout, sx = (float)Win / (float)Wout;
     constexpr int VN = Vec16<T>::N;
-    const int vec_ok = (Win % VN == 0) && aligned16(in);
-    const int rw = (int)(RS_TO * sx) + 6 + 2 * VN;          // staged row: tile span + taps + alignment slack
-    const int rw_pad = (rw + 3) / 4 * 4 + 4;
+    const int rw = (int)(RS_TO * sx) + 6;                    // staged row: tile span + 4 taps (+ slack)
     const int rh = (int)(RS_TO * sy) + 6;
-    const size_t smem = ((size_t)rw_pad * rh + RS_TO * 8) * sizeof(float);
-    DD_REQUIRE(smem <= 200 * 1024, DD_EUNSUPPORTED, "dd_bicubic_resize_fwd: scale %.2fx%.2f needs %zu bytes of shared memory", sy, sx, smem);
+    const int tp = rh | 1;
     const int tiles_x = (Wout + RS_TO - 1) / RS_TO, tiles_y = (Hout + RS_TO - 1) / RS_TO;
     const int64_t blocks = planes * tiles_x * tiles_y;
     DD_REQUIRE(blocks < (1ll << 31), DD_EUNSUPPORTED, "dd_bicubic_resize_fwd: too many tiles");
+    if ((Win % VN == 0) && aligned16(in)) {
+        const int S = (((rw + 2 * VN + 4 + 3) / 4) | 1) * 4;   // + alignment slack on both sides + the second float4 of the last tap
+        const size_t smem = ((size_t)S * rh + (size_t)RS_TO * tp + RS_TO * 10) * sizeof(float);
+        if (smem <= 100 * 1024) {
+            auto kern = bicubic_fwd_vec_kernel<T>;
+            DD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<(unsigned)blocks, RS_THREADS, smem, st>>>((const T*)in, (T*)out, Hin, Win, Hout, Wout, sy, sx, tiles_x, tiles_y, S, rh, tp);
+            DD_LAUNCH_OK();
+            return 0;
+        }
+    }
+    const int rw_pad = rw | 1;                               // odd stride
+    const size_t smem = ((size_t)rw_pad * rh + (size_t)RS_TO * tp + RS_TO * 10) * sizeof(float);
+    DD_REQUIRE(smem <= 200 * 1024, DD_EUNSUPPORTED, "dd_bicubic_resize_fwd: scale %.2fx%.2f needs %zu bytes of shared memory", sy, sx, smem);
     auto kern = bicubic_fwd_kernel<T>;
     DD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)blocks, RS_THREADS, smem, st>>>((const T*)in, (T*)out, Hin, Win, Hout, Wout, sy, sx, tiles_x, tiles_y, rw_pad, rh, vec_ok);
+    kern<<<(unsigned)blocks, RS_THREADS, smem, st>>>((const T*)in, (T*)out, Hin, Win, Hout, Wout, sy, sx, tiles_x, tiles_y, rw_pad, rh, tp);
     DD_LAUNCH_OK();
+    return 0;
+}
+
+template <typename T, int MC>
+static int launch_bwd_fast(const void* gout, void* gin, int64_t planes, int Hin, int Win, int Hout, int Wout, cudaStream_t st, bool& done) {
+    const float sy = (float)Hin / (float)Hout, sx = (float)Win / (float)Wout;
+    constexpr int VN = Vec16<T>::N;
+    const bool vec = (Wout % VN == 0) && aligned16(gout);
+    int gw_max = out_span(RS_BX, sx), GW = gw_max + MC;
+    if (vec) {
+        gw_max = (gw_max + VN - 1 + VN - 1) / VN * VN;          // region start aligned down, width in whole vectors
+        GW = (gw_max + MC + VN - 1) / VN * VN;
+        if (VN == 4) GW = ((GW / 4) | 1) * 4;                    // 4 * odd: two rows of a warp never share a bank
+    }
+    int by = Hin < 128 ? (Hin + 3) / 4 * 4 : 128, gh_max = 0;
+    size_t smem = 0;
+    for (; by >= 8; by /= 2) {
+        gh_max = out_span(by, sy);
+        smem = ((size_t)(gw_max + gh_max + RS_BX + by) * 5 + (size_t)gh_max * GW + (size_t)(gh_max + MC) * RS_BX) * sizeof(float);
+        if (smem <= 56 * 1024) break;
+    }
+    done = false;
+    if (by < 8) return 0;                      // region does not fit: generic path
+    const int tiles_x = (Win + RS_BX - 1) / RS_BX, tiles_y = (Hin + by - 1) / by;
+    const int64_t blocks = planes * tiles_x * tiles_y;
+    DD_REQUIRE(blocks < (1ll << 31), DD_EUNSUPPORTED, "dd_bicubic_resize_bwd: too many tiles");
+    auto kern = vec ? bicubic_bwd_fast_kernel<T, MC, true> : bicubic_bwd_fast_kernel<T, MC, false>;
+    DD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int vec_ok = (Win % 4 == 0) && aligned16(gin);   // 4-column stores: 16 B (fp32) / 8 B (16-bit) aligned
+    kern<<<(unsigned)blocks, RS_THREADS, smem, st>>>((const T*)gout, (T*)gin, Hin, Win, Hout, Wout, sy, sx, tiles_x, tiles_y, gw_max, gh_max, by,
+                                                    vec_ok, GW);
+    DD_LAUNCH_OK();
+    done = true;
     return 0;
 }
 
 template <typename T>
 static int launch_bwd(const void* gout, void* gin, int64_t planes, int Hin, int Win, int Hout, int Wout, cudaStream_t st) {
     const float sy = (float)Hin / (float)Hout, sx = (float)Win / (float)Wout;
+    {   // fast path: at most 4 outputs touch any input index along either axis
+        const int mc = std::max(max_candidates(Win, Wout), max_candidates(Hin, Hout));
+        bool done = false;
+        int rc = 0;
+        if (mc <= 2) rc = launch_bwd_fast<T, 2>(gout, gin, planes, Hin, Win, Hout, Wout, st, done);
+        else if (mc <= 4) rc = launch_bwd_fast<T, 4>(gout, gin, planes, Hin, Win, Hout, Wout, st, done);
+        if (rc != 0 || done) return rc;
+    }
     const int mcx = cand(sx), mcy = cand(sy);
     const int gw_max = out_span(RS_BX, sx);
     int by = RS_BY, gh_max = 0;

@@ -58,3 +58,37 @@ def test_cuda_graph_step_matches_eager(cuda_device, tmp_path, monkeypatch):
         outs.append((img.clone(), lat.clone()))
     assert torch.allclose(outs[0][1], outs[1][1], rtol=1e-4, atol=1e-5)
     assert outs[0][0].min() >= 0 and outs[0][0].max() <= 1
+
+
+def test_config5_guidance_every_step_bf16(cuda_device, tmp_path, monkeypatch):
+    """BASELINE configs[4] in miniature: 1000-class prototype tables, bf16 networks, `direct_guidance` on ALL 50 steps
+    (--strength 1.0 --guidance_step 50 --guidance_period 50, SURVEY section 7 'timestep-index arithmetic').  Every step
+    must be guided, scores finite, and the first guided step must agree with the fp32 run to bf16 accuracy."""
+    import generate_data as gd
+    from distdiff_b200 import expand, nets, ops
+    from distdiff_b200.scheduler import DDIMScheduler
+    monkeypatch.chdir(tmp_path)
+    base = [a for a in COMMON if a not in ("transform_guidance",)]
+    args = gd.parse_args(base + ["--guidance_type", "direct_guidance", "--output_dir", "o"])
+    args.strength, args.guidance_step, args.guidance_period, args.synthetic_classes = 1.0, 50, 50, 1000
+    unet, vae, guide = gd.build_models(args, cuda_device, torch.float32)
+    g = torch.Generator().manual_seed(3)
+    gproto = ops.normalize_rows(torch.randn(1000, 512, generator=g).to(cuda_device))
+    lproto = ops.normalize_rows(torch.randn(1000, 2, 512, generator=g).to(cuda_device))
+    batch = {"input_ids": torch.randn(2, 77, 768, generator=g), "uncond_inputs_ids": torch.randn(2, 77, 768, generator=g),
+             "image_latents": torch.randn(2, 4, 8, 8, generator=g), "targets": [999, 417], "class_names": ["a", "b"],
+             "image_paths": ["x.jpg", "y.jpg"]}
+    first = {}
+    for wd in (torch.float32, torch.bfloat16):
+        expand.set_seed(5)
+        for m in (unet, vae):
+            m.to(wd)
+        ex = expand.Expander(args, unet, vae, guide.to(wd), nets.VaeImageProcessor(), DDIMScheduler(), gproto, lproto,
+                             weight_dtype=wd, device=cuda_device, use_cuda_graph=False)
+        img, lat, info = ex.expand_batch(batch, 0)
+        assert info["guide_timesteps"] == [981 - 20 * i for i in range(50)] and len(info["scores"]) == 50
+        sc = torch.stack([s.float() for s in info["scores"]])
+        assert bool(torch.isfinite(sc).all()) and bool(torch.isfinite(lat.float()).all()) and bool(torch.isfinite(img.float()).all())
+        assert img.shape[0] == 2 and float(img.min()) >= 0.0 and float(img.max()) <= 1.0
+        first[wd] = float(sc[0])
+    assert abs(first[torch.bfloat16] - first[torch.float32]) <= 5e-2 * abs(first[torch.float32])

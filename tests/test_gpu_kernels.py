@@ -181,7 +181,8 @@ def _energy_case(B, C, K, D, seed, dup=False):
 
 
 @pytest.mark.parametrize("B,C,K,D", [(1, 5, 3, 64), (2, 100, 3, 2048), (16, 100, 3, 2048), (7, 10, 10, 1280),
-                                     (5, 4, 1, 512), (1024, 100, 3, 2048), (2000, 50, 10, 2048), (1500, 7, 5, 512)])
+                                     (5, 4, 1, 512), (1024, 100, 3, 2048), (2000, 50, 10, 2048), (1500, 7, 5, 512),
+                                     (64, 1000, 3, 2048)])   # last: ImageNet-scale tables, BASELINE configs[4]
 @pytest.mark.parametrize("normalize_f", [False, True])
 def test_energy_vs_oracle(ops, cuda_device, B, C, K, D, normalize_f):
     f, gp, lp, y = _energy_case(B, C, K, D, 10 + B)

@@ -328,6 +328,16 @@ def run_ours(opt):
                 "regime": f"launch-latency-bound: at B={opt.batch} the kernel moves {dk['bytes'] // dk['launches'] // 1024} KB per launch "
                           "(HBM-bound sizes are in roofline_batched)",
                 "measured": "CUDA events around each launch on the launching stream, one instrumented eager step after the timed region"}
+    # dram bytes per launch of the dominant kernel from the committed `ncu --set full` capture of the same launch
+    # shape (tools/instep_k5.py); null when this run's batch / dtype has no capture
+    try:
+        with open(os.path.join(ROOT, "profiles", "instep_traffic.json")) as fh:
+            cap = json.load(fh).get(f"{dom}:B{opt.batch}:{opt.dtype}")
+        if cap:
+            roofline["traffic"] = cap["dram_bytes_per_launch"]
+            roofline["traffic_source"] = cap["source"]
+    except (OSError, ValueError):
+        pass
     kernels_in_step = {k: {"launches": v["launches"], "avg_us": round(1e3 * v["ms"] / v["launches"], 2),
                            "GBps": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1)} for k, v in per_kernel.items()}
 

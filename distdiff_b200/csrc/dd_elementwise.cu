@@ -37,17 +37,19 @@ __device__ __forceinline__ void ddim_math(float u, float t, float x, float g, co
     if (has_grad) prev = __fsub_rn(prev, __fmul_rn(c.rho, g));                        // generate_data.py:762
 }
 
-template <typename T, bool HAS_TEXT, bool HAS_GRAD>
+// EW_UNROLL = ew_unroll<T>() with 256-thread CTAs for HBM-bound sizes; EW_UNROLL = 1 with 64/128-thread CTAs for the
+// in-step sizes (B <= 16 latents = 0.3-2.6 MB), where spreading the launch over all SMs shortens the kernel
+template <typename T, bool HAS_TEXT, bool HAS_GRAD, int EW_UNROLL>
 __global__ void __launch_bounds__(EW_THREADS)
 cfg_ddim_fwd_vec(const T* __restrict__ nu, const T* __restrict__ nt, const T* __restrict__ x,
                  const T* __restrict__ grad, T* __restrict__ x_prev, T* __restrict__ x0, int64_t nvec, DdimScalars c) {
     using V = Vec16<T>;
-    constexpr int EW_UNROLL = ew_unroll<T>();
-    const int64_t base = (int64_t)blockIdx.x * (EW_THREADS * EW_UNROLL) + threadIdx.x;
+    const int nthr = blockDim.x;
+    const int64_t base = (int64_t)blockIdx.x * (nthr * EW_UNROLL) + threadIdx.x;
     V a[EW_UNROLL], b[EW_UNROLL], xx[EW_UNROLL], gg[EW_UNROLL];
 #pragma unroll
     for (int j = 0; j < EW_UNROLL; ++j) {
-        const int64_t i = base + (int64_t)j * EW_THREADS;
+        const int64_t i = base + (int64_t)j * nthr;
         if (i < nvec) {
             a[j].load(nu + i * V::N);
             if (HAS_TEXT) b[j].load(nt + i * V::N);
@@ -57,7 +59,7 @@ cfg_ddim_fwd_vec(const T* __restrict__ nu, const T* __restrict__ nt, const T* __
     }
 #pragma unroll
     for (int j = 0; j < EW_UNROLL; ++j) {
-        const int64_t i = base + (int64_t)j * EW_THREADS;
+        const int64_t i = base + (int64_t)j * nthr;
         if (i < nvec) {
             V p, o;
 #pragma unroll
@@ -311,11 +313,20 @@ static int cfg_ddim_fwd_t(const void* nu, const void* nt, const void* x, int64_t
                      aligned16(x_prev) && aligned16(x0);
     if (vec) {
         const int64_t nvec = n / V::N;
-        const unsigned grid = vec_blocks(nvec, EW_UNROLL);
-        if (nt && grad) cfg_ddim_fwd_vec<T, true, true><<<grid, EW_THREADS, 0, st>>>(pnu, pnt, px, pg, pp, p0, nvec, c);
-        else if (nt) cfg_ddim_fwd_vec<T, true, false><<<grid, EW_THREADS, 0, st>>>(pnu, pnt, px, pg, pp, p0, nvec, c);
-        else if (grad) cfg_ddim_fwd_vec<T, false, true><<<grid, EW_THREADS, 0, st>>>(pnu, pnt, px, pg, pp, p0, nvec, c);
-        else cfg_ddim_fwd_vec<T, false, false><<<grid, EW_THREADS, 0, st>>>(pnu, pnt, px, pg, pp, p0, nvec, c);
+        if (nvec < (int64_t)2 * 148 * EW_THREADS * EW_UNROLL) {   // in-step sizes: one vector per thread, >= 128 small CTAs
+            const int thr = nvec <= 16384 ? 64 : 128;
+            const unsigned grid = (unsigned)((nvec + thr - 1) / thr);
+            if (nt && grad) cfg_ddim_fwd_vec<T, true, true, 1><<<grid, thr, 0, st>>>(pnu, pnt, px, pg, pp, p0, nvec, c);
+            else if (nt) cfg_ddim_fwd_vec<T, true, false, 1><<<grid, thr, 0, st>>>(pnu, pnt, px, pg, pp, p0, nvec, c);
+            else if (grad) cfg_ddim_fwd_vec<T, false, true, 1><<<grid, thr, 0, st>>>(pnu, pnt, px, pg, pp, p0, nvec, c);
+            else cfg_ddim_fwd_vec<T, false, false, 1><<<grid, thr, 0, st>>>(pnu, pnt, px, pg, pp, p0, nvec, c);
+        } else {
+            const unsigned grid = vec_blocks(nvec, EW_UNROLL);
+            if (nt && grad) cfg_ddim_fwd_vec<T, true, true, EW_UNROLL><<<grid, EW_THREADS, 0, st>>>(pnu, pnt, px, pg, pp, p0, nvec, c);
+            else if (nt) cfg_ddim_fwd_vec<T, true, false, EW_UNROLL><<<grid, EW_THREADS, 0, st>>>(pnu, pnt, px, pg, pp, p0, nvec, c);
+            else if (grad) cfg_ddim_fwd_vec<T, false, true, EW_UNROLL><<<grid, EW_THREADS, 0, st>>>(pnu, pnt, px, pg, pp, p0, nvec, c);
+            else cfg_ddim_fwd_vec<T, false, false, EW_UNROLL><<<grid, EW_THREADS, 0, st>>>(pnu, pnt, px, pg, pp, p0, nvec, c);
+        }
     } else {
         cfg_ddim_fwd_scalar<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pnu, pnt, px, pg, pp, p0, n, c);
     }

@@ -46,6 +46,14 @@ SIGNATURES = {
     "dd_comm_init": (_i, [_i, _i, _p, C.POINTER(_p)]),
     "dd_comm_allreduce": (_i, [_p, _p, _z, _p, _z, _p]),
     "dd_comm_destroy": (_i, [_p]),
+    "dd_peer_create": (_i, [_i, _i, _z, C.POINTER(_p), _p]),
+    "dd_peer_connect": (_i, [_p, _p]),
+    "dd_peer_local": (_p, [_p]),
+    "dd_peer_header_bytes": (_z, []),
+    "dd_peer_kmeans_exchange": (_i, [_p, _z, _z, _z, _z, _z, _i, _i, _p]),
+    "dd_peer_status": (_i, [_p, _p, C.POINTER(_i)]),
+    "dd_kmeans_lloyd": (_i, [_p, _p, _l, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _z, _p, _p, _i, _p]),
+    "dd_peer_destroy": (_i, [_p]),
 }
 
 _lib = None

@@ -119,6 +119,20 @@ __device__ __forceinline__ T warp_sum(T v) {
     return v;
 }
 
+// fp64 sum over a 256-thread CTA (8 warps), fixed order; shared by the row kernels of dd_proto.cu and dd_peer.cu
+__device__ __forceinline__ double block_sum_f64(double v, double* sh /* [8] */) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) sh[w] = v;
+    __syncthreads();
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sh[i];
+    return t;
+}
+
 // x / d through a precomputed reciprocal + one Newton correction step (3 FMA-pipe instructions instead of the
 // ~10-instruction IEEE division sequence); returns the correctly rounded quotient except in rare
 // double-rounding corner cases (<= 1 ulp there).

@@ -760,19 +760,6 @@ partial_reduce_kernel(const double* __restrict__ ws_sum, const int64_t* __restri
 // ---------------------------------------------------------------------------------------------------
 // K2 and small row kernels (one CTA per row; tables are C*K rows -- tiny)
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double block_sum_f64(double v, double* sh) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    __syncthreads();
-    if (l == 0) sh[w] = v;
-    __syncthreads();
-    double t = 0.0;
-#pragma unroll
-    for (int i = 0; i < PK_WARPS; ++i) t += sh[i];
-    return t;
-}
-
 __global__ void __launch_bounds__(PK_THREADS)
 class_mean_kernel(const double* __restrict__ sum, const int64_t* __restrict__ cnt, int D, float* __restrict__ mean,
                   float* __restrict__ mean_unit) {

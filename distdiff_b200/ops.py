@@ -411,13 +411,19 @@ def normalize_rows(t: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def kmeans_seed(x_sorted: torch.Tensor, row_idx: torch.Tensor):
+def kmeans_seed(x_sorted: torch.Tensor, row_idx: torch.Tensor, out=None):
+    """Seed rows -> (sum [.., D] f64 = the row or 0, cnt [..] i64 = 1 or 0); ``out=(sum, cnt)`` writes in place."""
     x_sorted = _req(x_sorted, "x_sorted", torch.float32)
     row_idx = _req(row_idx, "row_idx", torch.int64)
     D = x_sorted.shape[1]
     R = row_idx.numel()
-    s = torch.empty(*row_idx.shape, D, dtype=torch.float64, device=x_sorted.device)
-    c = torch.empty(row_idx.shape, dtype=torch.int64, device=x_sorted.device)
+    if out is None:
+        s = torch.empty(*row_idx.shape, D, dtype=torch.float64, device=x_sorted.device)
+        c = torch.empty(row_idx.shape, dtype=torch.int64, device=x_sorted.device)
+    else:
+        s, c = _req(out[0], "sum", torch.float64), _req(out[1], "cnt", torch.int64)
+        if s.numel() != R * D or c.numel() != R or s.data_ptr() != out[0].data_ptr():
+            raise DistDiffError("kmeans_seed: out buffers must be contiguous [R, D] f64 / [R] i64")
     _call("dd_kmeans_seed", R * D * 12, 1,
           _ptr(x_sorted), _ptr(row_idx), R, D, _ptr(s), _ptr(c), _stream())
     return s, c
@@ -431,16 +437,30 @@ def kmeans_update(sum_: torch.Tensor, cnt: torch.Tensor, centroid: torch.Tensor,
 
 
 class KMeansBuffers:
-    """Caller-owned buffers of one k-means problem (allocated once, reused every Lloyd iteration)."""
+    """Caller-owned buffers of one k-means problem (allocated once, reused every Lloyd iteration).  With ``arena`` (a
+    PeerArena) the buffers every rank exchanges live in the IPC-shared arena, at the same offsets on all ranks."""
 
-    def __init__(self, N: int, D: int, C_: int, K: int, device):
-        self.centroid = torch.zeros(C_, K, D, dtype=torch.float32, device=device)
-        self.cnorm = torch.zeros(C_, K, dtype=torch.float32, device=device)
+    def __init__(self, N: int, D: int, C_: int, K: int, device, arena=None):
+        self.arena = arena
+        if arena is None:
+            self.centroid = torch.zeros(C_, K, D, dtype=torch.float32, device=device)
+            self.cnorm = torch.zeros(C_, K, dtype=torch.float32, device=device)
+            self.sum = torch.empty(C_, K, D, dtype=torch.float64, device=device)
+            self.cnt = torch.empty(C_, K, dtype=torch.int64, device=device)
+            self.gcnt = None
+        else:   # arena memory is zero-initialised by dd_peer_create
+            self.sum = arena.carve((C_, K, D), torch.float64)
+            self.cnt = arena.carve((C_, K), torch.int64)
+            self.centroid = arena.carve((C_, K, D), torch.float32)
+            self.cnorm = arena.carve((C_, K), torch.float32)
+            self.gcnt = arena.carve((C_, K), torch.int64)
         self.assign = torch.empty(N, dtype=torch.int32, device=device)
-        self.sum = torch.empty(C_, K, D, dtype=torch.float64, device=device)
-        self.cnt = torch.empty(C_, K, dtype=torch.int64, device=device)
         self.inertia = torch.empty(1, dtype=torch.float64, device=device)
         self.ws = proto_workspace(D, C_, K, device)
+
+    @staticmethod
+    def arena_bytes(D: int, C_: int, K: int) -> int:
+        return C_ * K * (D * 12 + 20) + 5 * 256
 
 
 def kmeans_assign_accum(x_sorted: torch.Tensor, class_off: torch.Tensor, buf: KMeansBuffers, want_inertia: bool = False) -> None:
@@ -453,6 +473,20 @@ def kmeans_assign_accum(x_sorted: torch.Tensor, class_off: torch.Tensor, buf: KM
           _ptr(x_sorted), _ptr(class_off), N, D, Cn, K, _ptr(buf.centroid), _ptr(buf.cnorm),
                                             _ptr(buf.assign), _ptr(buf.sum), _ptr(buf.cnt), _ptr(buf.inertia) if want_inertia else None, _ptr(buf.ws),
                                             buf.ws.numel(), _stream())
+
+
+def kmeans_lloyd(x_sorted: torch.Tensor, class_off: torch.Tensor, buf: KMeansBuffers, iters: int, comm=None) -> None:
+    """``iters`` Lloyd iterations launched back to back from C (dd_kmeans_lloyd): K3 pass + exchange per iteration.
+    Exchange: the fused peer kernel when the buffers live in a PeerArena, else NCCL all-reduce (``comm``: an ops.Comm)
+    + update, else the update alone (single GPU)."""
+    x_sorted = _req(x_sorted, "x_sorted", torch.float32)
+    N, D = x_sorted.shape
+    Cn, K, _ = buf.centroid.shape
+    peer = buf.arena.ctx if buf.arena is not None else None
+    nccl = comm.handle if (comm is not None and peer is None) else None
+    _call("dd_kmeans_lloyd", int(iters) * (N * D * 4 + 2 * N * 4), 3 * int(iters),
+          _ptr(x_sorted), _ptr(class_off), N, D, Cn, K, _ptr(buf.centroid), _ptr(buf.cnorm), _ptr(buf.assign), _ptr(buf.sum),
+          _ptr(buf.cnt), _ptr(buf.gcnt), _ptr(buf.ws), buf.ws.numel(), nccl, peer, int(iters), _stream())
 
 
 def agglo_average(x_sorted: torch.Tensor, class_off: torch.Tensor, K: int, max_class_size: int):
@@ -504,3 +538,72 @@ class Comm:
         if self.handle:
             check(_lib.lib().dd_comm_destroy(self.handle), "dd_comm_destroy")
             self.handle = None
+
+
+# ------------------------------------------------------------------------------------------------
+# fused centroid exchange over NVLink peer memory (csrc/dd_peer.cu)
+# ------------------------------------------------------------------------------------------------
+class _DeviceSpan:
+    """Raw device memory as a `__cuda_array_interface__` object so torch can view it (the arena is cudaMalloc'ed by
+    the library because it has to be IPC-exportable; torch's caching allocator sub-allocates and cannot be)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3, "strides": None}
+
+
+class PeerArena:
+    """One IPC-shared arena per rank; ``allgather_bytes(b) -> [bytes per rank]`` is the host exchange of the handles."""
+
+    def __init__(self, rank: int, world: int, nbytes: int, allgather_bytes, device):
+        self.rank, self.world, self.device = rank, world, torch.device(device)
+        L = _lib.lib()
+        self.header = int(L.dd_peer_header_bytes())
+        self.nbytes = int(nbytes) + self.header
+        handle = (C.c_ubyte * 64)()
+        ctx = C.c_void_p()
+        check(L.dd_peer_create(rank, world, self.nbytes, C.byref(ctx), handle), "dd_peer_create")
+        self.ctx = ctx
+        blobs = allgather_bytes(bytes(handle))
+        if len(blobs) != world or any(len(b) != 64 for b in blobs):
+            raise DistDiffError("PeerArena: the handle exchange must return one 64-byte handle per rank")
+        check(L.dd_peer_connect(self.ctx, b"".join(blobs)), "dd_peer_connect")
+        self._span = _DeviceSpan(int(L.dd_peer_local(self.ctx)), self.nbytes)
+        self.bytes_view = torch.as_tensor(self._span, device=self.device)
+        self._cursor = self.header
+
+    def reset(self) -> None:
+        """Forget the carved buffers (the next problem re-carves from the start; flags and epoch carry on)."""
+        self._cursor = self.header
+
+    @property
+    def capacity(self) -> int:
+        return self.nbytes - self.header
+
+    def carve(self, shape, dtype) -> torch.Tensor:
+        n = 1
+        for d in shape:
+            n *= int(d)
+        nb = n * torch.empty((), dtype=dtype).element_size()
+        off = (self._cursor + 255) // 256 * 256
+        if off + nb > self.nbytes:
+            raise DistDiffError("PeerArena: out of space")
+        self._cursor = off + nb
+        t = self.bytes_view[off:off + nb].view(dtype).view(*shape)
+        t._dd_arena_offset = off
+        return t
+
+    def kmeans_exchange(self, sum_, cnt, centroid, cnorm, gcnt) -> None:
+        R, D = cnt.numel(), sum_.shape[-1]
+        _call("dd_peer_kmeans_exchange", 0, 1, self.ctx, sum_._dd_arena_offset, cnt._dd_arena_offset, centroid._dd_arena_offset,
+              cnorm._dd_arena_offset, gcnt._dd_arena_offset, R, D, _stream())
+
+    def status(self) -> int:
+        v = C.c_int(0)
+        check(_lib.lib().dd_peer_status(self.ctx, _stream(), C.byref(v)), "dd_peer_status")
+        return int(v.value)
+
+    def close(self) -> None:
+        if self.ctx:
+            self.bytes_view = None
+            check(_lib.lib().dd_peer_destroy(self.ctx), "dd_peer_destroy")
+            self.ctx = None

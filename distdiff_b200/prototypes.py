@@ -40,6 +40,22 @@ class Collective:
     def allgather_rows(self, t: torch.Tensor) -> torch.Tensor:  # concat along dim 0 in rank order (ragged ok)
         return t
 
+    # the per-iteration exchange of the sharded k-means: local partial sums / counts in buf.sum / buf.cnt ->
+    # the same centroids + norms on every rank.  Default: all-reduce (SUM) + K2-style update kernel.
+    def kmeans_buffers(self, N: int, D: int, C_: int, K: int, device):
+        return ops.KMeansBuffers(N, D, C_, K, device)
+
+    def kmeans_exchange(self, buf) -> None:
+        self.allreduce(buf.sum, buf.cnt)
+        ops.kmeans_update(buf.sum, buf.cnt, buf.centroid, buf.cnorm)
+
+    def kmeans_lloyd(self, xs, off, buf, iters: int) -> None:
+        """``iters`` x (K3 pass + exchange).  Single GPU: one C call launches all of it."""
+        ops.kmeans_lloyd(xs, off, buf, iters)
+
+    def finish(self) -> None:
+        return None
+
 
 class TorchDistCollective(Collective):
     """torch.distributed plumbing (NCCL on the GPUs; gloo in the CPU tests of the sharding logic)."""
@@ -53,6 +69,11 @@ class TorchDistCollective(Collective):
         for t in (sum_, cnt):
             if t is not None:
                 self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+
+    def kmeans_lloyd(self, xs, off, buf, iters):
+        for _ in range(int(iters)):
+            ops.kmeans_assign_accum(xs, off, buf)
+            self.kmeans_exchange(buf)
 
     def allgather_rows(self, t):
         n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
@@ -86,6 +107,52 @@ class NcclCollective(TorchDistCollective):
     def allreduce(self, sum_, cnt):
         self.comm.allreduce(sum_, cnt)
 
+    def kmeans_lloyd(self, xs, off, buf, iters):
+        ops.kmeans_lloyd(xs, off, buf, iters, comm=self.comm)
+
+
+class PeerCollective(NcclCollective):
+    """NcclCollective whose per-iteration k-means exchange is the fused peer-memory kernel (csrc/dd_peer.cu): flag
+    barrier + reduce-scatter by NVLink loads in rank order + centroid update + all-gather of fp32 centroid rows by
+    NVLink stores, one launch per rank, instead of an NCCL all-reduce of fp64 sums followed by the update kernel.
+    The one-off class-sum all-reduce and the ragged all-gathers stay on NCCL."""
+
+    def __init__(self):
+        super().__init__()
+        self.arena = None
+
+    def _allgather_bytes(self, b: bytes):
+        out = [None] * self.world
+        self.dist.all_gather_object(out, b)
+        return out
+
+    def kmeans_buffers(self, N, D, C_, K, device):
+        need = ops.KMeansBuffers.arena_bytes(D, C_, K)
+        if self.arena is not None and self.arena.capacity >= need:
+            self.arena.reset()           # same arena, same offsets on every rank (all ranks make the same calls)
+        else:
+            if self.arena is not None:
+                self.dist.barrier()      # peers may still have the old arena mapped in a running kernel
+                self.arena.close()
+            self.arena = ops.PeerArena(self.rank, self.world, need, self._allgather_bytes, device)
+        return ops.KMeansBuffers(N, D, C_, K, device, arena=self.arena)
+
+    def kmeans_exchange(self, buf) -> None:
+        self.arena.kmeans_exchange(buf.sum, buf.cnt, buf.centroid, buf.cnorm, buf.gcnt)
+
+    def finish(self) -> None:
+        if self.arena is not None:
+            st = self.arena.status()
+            if st != 0:
+                raise DistDiffError(f"peer exchange: flag wait timed out (status {st}); a rank is missing or made a different call sequence")
+
+    def close(self) -> None:
+        if self.arena is not None:
+            self.dist.barrier()          # nobody may still have this arena mapped in a running kernel
+            self.arena.close()
+            self.arena = None
+        self.comm.close()
+
 
 def _class_shard(counts: np.ndarray, world: int):
     """Contiguous class ranges balanced by sum n_c^2 (the agglomerative cost)."""
@@ -101,6 +168,16 @@ def _class_shard(counts: np.ndarray, world: int):
         bounds.append(len(counts))
     bounds[-1] = len(counts)
     return bounds
+
+
+def seed_rows(off: torch.Tensor, local_counts: torch.Tensor, before: torch.Tensor, total: torch.Tensor, K: int) -> torch.Tensor:
+    """[C,K] local row (in the class-sorted shard) of every k-means seed this rank owns, -1 elsewhere.  The seed of
+    cluster k of class c is the floor(k*n_c/K)-th row of the class in GLOBAL dataset order (oracle/prototypes.py)."""
+    kk = torch.arange(K, device=off.device)[None, :]
+    gpos = (kk * total[:, None]) // K                                          # [C,K] position inside the class
+    lpos = gpos - before[:, None]
+    mine = (lpos >= 0) & (lpos < local_counts[:, None])
+    return torch.where(mine, off[:-1, None] + lpos, torch.full_like(lpos, -1)).contiguous()
 
 
 def build_prototypes(features: torch.Tensor, labels: torch.Tensor, num_classes: int, K: int,
@@ -154,7 +231,7 @@ def build_prototypes(features: torch.Tensor, labels: torch.Tensor, num_classes: 
         debug.update(labels_sorted=labels_sorted, x_sorted=xs, class_off=off)
     elif cluster_method == "kmeans":                                            # K3 (north-star extension)
         N, D = xs.shape
-        buf = ops.KMeansBuffers(N, D, C_, K, dev)
+        buf = coll.kmeans_buffers(N, D, C_, K, dev)
         # seed: the floor(k*n_c/K)-th row of class c in GLOBAL dataset order; shards are contiguous blocks of the
         # dataset, so global order inside a class = rank order, then local order
         local_counts = (off[1:] - off[:-1])
@@ -164,23 +241,20 @@ def build_prototypes(features: torch.Tensor, labels: torch.Tensor, num_classes: 
         else:
             before = torch.zeros_like(local_counts)
         total = torch.from_numpy(counts).to(dev)
-        kk = torch.arange(K, device=dev)[None, :]
-        gpos = (kk * total[:, None]) // K                                      # [C,K] position inside the class
-        lpos = gpos - before[:, None]
-        mine = (lpos >= 0) & (lpos < local_counts[:, None])
-        row_idx = torch.where(mine, off[:-1, None] + lpos, torch.full_like(lpos, -1)).contiguous()
-        s, n = ops.kmeans_seed(xs, row_idx)
-        coll.allreduce(s, n)
-        ops.kmeans_update(s, n, buf.centroid, buf.cnorm)
+        row_idx = seed_rows(off, local_counts, before, total, K)
+        ops.kmeans_seed(xs, row_idx, out=(buf.sum, buf.cnt))
+        coll.kmeans_exchange(buf)                                              # seed rows -> centroids on every rank
         inertia = []
-        for _ in range(int(kmeans_iters)):
-            ops.kmeans_assign_accum(xs, off, buf, want_inertia=return_debug)   # K3
-            coll.allreduce(buf.sum, buf.cnt)                                   # centroid sums + counts over NVLink
-            ops.kmeans_update(buf.sum, buf.cnt, buf.centroid, buf.cnorm)
-            if return_debug:
+        if return_debug:                                                       # per-iteration inertia: step by step
+            for _ in range(int(kmeans_iters)):
+                ops.kmeans_assign_accum(xs, off, buf, want_inertia=True)       # K3
+                coll.kmeans_exchange(buf)                                      # centroid sums + counts over NVLink
                 inertia.append(buf.inertia.clone())
-        lmean = buf.centroid
-        debug.update(labels_sorted=buf.assign, inertia=inertia, counts=buf.cnt)
+        else:
+            coll.kmeans_lloyd(xs, off, buf, int(kmeans_iters))                 # all iterations launched from one C call
+        coll.finish()
+        lmean = buf.centroid.clone() if buf.arena is not None else buf.centroid
+        debug.update(labels_sorted=buf.assign, inertia=inertia, counts=buf.gcnt if buf.gcnt is not None else buf.cnt)
     else:
         raise ValueError(f"unknown cluster_method {cluster_method!r} (agglomerative | kmeans)")
     if return_debug:

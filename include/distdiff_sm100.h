@@ -10,7 +10,8 @@
  *
  * Conventions
  *  - plain C: device pointers + sizes; no torch / C++ types.  Buffers are contiguous and owned by the
- *    caller, including workspaces; the library allocates nothing persistent except NCCL communicators.
+ *    caller, including workspaces; the library allocates nothing persistent except NCCL communicators and the
+ *    peer-exchange arena (dd_peer_create), which must be IPC-exportable and therefore cannot come from the caller.
  *  - every call is asynchronous on the given stream (a cudaStream_t passed as void*); no hidden syncs.
  *  - return 0 on success, otherwise a non-zero code (cudaError_t, or 1000+ncclResult_t, or DD_E*);
  *    the message is in dd_last_error() (thread-local).  Never throws, never exits.
@@ -171,6 +172,32 @@ int dd_comm_unique_id(void* unique_id_128);
 int dd_comm_init(int rank, int world, const void* unique_id_128, void** comm);
 int dd_comm_allreduce(void* comm, double* sum, size_t n_sum, int64_t* cnt, size_t n_cnt, dd_stream_t stream);
 int dd_comm_destroy(void* comm);
+
+/* ---- fused centroid exchange over NVLink peer memory (csrc/dd_peer.cu) --------------------------------
+ * The per-iteration exchange of the sharded k-means as ONE kernel per rank: flag barrier, reduce-scatter of the
+ * partial sums / counts by peer loads in rank order, centroid + norm (dd_kmeans_update's arithmetic), all-gather of
+ * the fp32 centroid rows by peer stores, flag barrier.  Replaces dd_comm_allreduce + dd_kmeans_update.
+ * dd_peer_create allocates this rank's arena (bytes, zeroed) and returns its 64-byte cudaIpcMemHandle_t; the host
+ * all-gathers the handles (world x 64 bytes, rank order) and passes them to dd_peer_connect.  The k-means buffers are
+ * carved out of the arena at the same offsets (>= dd_peer_header_bytes()) on every rank: sum [R,D] f64 and cnt [R]
+ * i64 hold the LOCAL partial results on entry; centroid [R,D] f32, cnorm [R] f32 and gcnt [R] i64 (global counts)
+ * are written for all R = C*K rows on every rank.  Every rank must make the same sequence of exchange calls.
+ * dd_peer_status: non-zero if a bounded flag wait timed out (synchronises the stream). */
+int dd_peer_create(int rank, int world, size_t bytes, void** ctx, void* ipc_handle_64);
+int dd_peer_connect(void* ctx, const void* all_handles);
+void* dd_peer_local(void* ctx);
+size_t dd_peer_header_bytes(void);
+int dd_peer_kmeans_exchange(void* ctx, size_t off_sum, size_t off_cnt, size_t off_centroid, size_t off_cnorm, size_t off_gcnt,
+                            int R, int D, dd_stream_t stream);
+int dd_peer_status(void* ctx, dd_stream_t stream, int* status);
+/* `iters` Lloyd iterations launched back to back from C (no host round trip between them): per iteration
+ * dd_kmeans_assign_accum, then the exchange -- dd_peer_kmeans_exchange when peer_ctx is given (sum / cnt / centroid /
+ * cnorm / gcnt must then lie inside the arena), else [dd_comm_allreduce when nccl_comm is given +] dd_kmeans_update.
+ * gcnt may be NULL without peer_ctx. */
+int dd_kmeans_lloyd(const float* x_sorted, const int64_t* class_off, int64_t N, int D, int C, int K, float* centroid, float* cnorm,
+                    int32_t* assign, double* sum, int64_t* cnt, int64_t* gcnt, void* ws, size_t ws_bytes, void* nccl_comm, void* peer_ctx,
+                    int iters, dd_stream_t stream);
+int dd_peer_destroy(void* ctx);
 
 #ifdef __cplusplus
 }

@@ -33,9 +33,12 @@ def class_mean(sum_, cnt, want_unit=True):
     return mean, (mean / mean.norm(dim=-1, keepdim=True) if want_unit else None)
 
 
-def kmeans_seed(x_sorted, row_idx):
+def kmeans_seed(x_sorted, row_idx, out=None):
     ok = row_idx >= 0
     s = torch.where(ok[..., None], x_sorted[row_idx.clamp(min=0)].double(), torch.zeros((), dtype=torch.float64))
+    if out is not None:
+        out[0].copy_(s); out[1].copy_(ok.to(torch.int64))
+        return out
     return s, ok.to(torch.int64)
 
 
@@ -53,6 +56,7 @@ class KMeansBuffers:
         self.sum = torch.zeros(C_, K, D, dtype=torch.float64)
         self.cnt = torch.zeros(C_, K, dtype=torch.int64)
         self.inertia = torch.zeros(1, dtype=torch.float64)
+        self.arena = self.gcnt = None
 
 
 def kmeans_assign_accum(x_sorted, class_off, buf, want_inertia=False):

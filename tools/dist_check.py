@@ -1,5 +1,6 @@
 """Run under torchrun (world >= 2): sharded prototype construction (samples sharded per GPU, NCCL all-reduce of
-class / centroid sums and counts through the C ABI) must reproduce the single-GPU result.
+class / centroid sums and counts through the C ABI, k-means centroids through the fused peer-memory exchange) must
+reproduce the single-GPU result; the peer exchange must give the NCCL path's assignments.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/dist_check.py
 """
@@ -19,7 +20,8 @@ def main():
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     dist.init_process_group("nccl", device_id=dev)
-    coll = prototypes.NcclCollective()
+    coll = prototypes.PeerCollective() if "--nccl-only" not in sys.argv else prototypes.NcclCollective()
+    nccl = prototypes.NcclCollective() if isinstance(coll, prototypes.PeerCollective) else None
     rng = np.random.default_rng(11)
     C, K, D, N = 12, 3, 512, 2400
     centers = rng.normal(size=(C, K, D)) * 4.0
@@ -37,9 +39,20 @@ def main():
         ok &= good
         if rank == 0:
             print(f"[dist_check] world={world} {method}: global rel err {eg:.2e}, local rel err {el:.2e} -> {'OK' if good else 'FAIL'}", flush=True)
+    if nccl is not None:   # fused peer-memory exchange vs NCCL all-reduce + update: same assignments, centroids to 1e-6
+        for K2 in (3, 5):
+            _, lp, dp = prototypes.build_prototypes(ft[sl].contiguous(), lt[sl].contiguous(), C, K2, "kmeans", 8, coll=coll, return_debug=True)
+            _, ln, dn = prototypes.build_prototypes(ft[sl].contiguous(), lt[sl].contiguous(), C, K2, "kmeans", 8, coll=nccl, return_debug=True)
+            e = float((lp - ln).abs().max() / ln.abs().max())
+            same = bool(torch.equal(dp["labels_sorted"], dn["labels_sorted"])) and bool(torch.equal(dp["counts"], dn["counts"]))
+            good = e <= 1e-6 and same
+            ok &= good
+            if rank == 0:
+                print(f"[dist_check] world={world} peer exchange vs NCCL, K={K2}: centroid rel err {e:.2e}, assignments/counts equal={same} -> {'OK' if good else 'FAIL'}", flush=True)
+        nccl.comm.close()
     flag = torch.tensor([int(ok)], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-    coll.comm.close()
+    coll.close() if hasattr(coll, "close") else coll.comm.close()
     dist.destroy_process_group()
     if int(flag) != 1:
         sys.exit(1)

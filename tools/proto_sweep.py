@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--ks", default="3,4,5,6,7,8,9,10")
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="per-iteration centroid exchange at world > 1")
     o = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", 1))
     rank = int(os.environ.get("RANK", 0))
@@ -39,7 +40,7 @@ def main():
     coll = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-        coll = prototypes.NcclCollective()
+        coll = prototypes.PeerCollective() if o.exchange == "peer" else prototypes.NcclCollective()
     g = torch.Generator(device=dev).manual_seed(7)
     feats = torch.randn(o.n, o.d, generator=g, device=dev)
     labels = (torch.arange(o.n, device=dev) % o.classes)
@@ -74,14 +75,14 @@ def main():
         gbs = nbytes / (it_ms * 1e-3) / 1e9
         if rank == 0:
             print(json.dumps({"config": "k-means sweep (BASELINE configs[3])", "N": o.n, "D": o.d, "C": o.classes, "K": K,
-                              "n_gpus": world, "lloyd_iters": o.iters, "ms_per_iteration": round(it_ms, 4),
+                              "n_gpus": world, "exchange": (o.exchange if world > 1 else "none"), "lloyd_iters": o.iters, "ms_per_iteration": round(it_ms, 4),
                               "ms_setup_K1_K2_seed": round(t0, 3), "ms_total": round(t1, 3), "GBps_aggregate": round(gbs, 1),
                               "frac_of_world_x_hbm_peak": round(gbs / (world * peak), 3), "hbm_peak_gbs": peak,
                               "peak_source": peak_src,
                               "includes": "K3 pass + fixed-order partial reduce + all-reduce of [C,K,D] f64 + [C,K] i64 + centroid update"}),
                   flush=True)
     if world > 1:
-        coll.comm.close()
+        coll.close() if hasattr(coll, "close") else coll.comm.close()
         dist.destroy_process_group()
 
 

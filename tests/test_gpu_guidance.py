@@ -180,6 +180,24 @@ def test_kmeans_prototypes_vs_oracle(cuda_device):
     assert all(inert[i + 1] <= inert[i] * (1 + 1e-6) for i in range(len(inert) - 1))   # Lloyd: monotone
 
 
+@pytest.mark.parametrize("K", [3, 7])
+def test_kmeans_lloyd_c_loop_matches_stepwise(cuda_device, K):
+    """dd_kmeans_lloyd (all iterations launched from one C call; the production path) gives the same centroids as the
+    step-by-step path the other tests inspect (which uses the inertia-reporting K3 variant)."""
+    from distdiff_b200 import prototypes
+    rng = np.random.default_rng(21)
+    C, D, per = 9, 1024, 700
+    centers = rng.normal(size=(C, K, D)) * 4.0                      # well separated: no near-ties to flip
+    labels = np.repeat(np.arange(C), per); rng.shuffle(labels)
+    feats = (centers[labels, rng.integers(0, K, size=len(labels))] + rng.normal(size=(len(labels), D))).astype(np.float32)
+    ft, lt = torch.from_numpy(feats).to(cuda_device), torch.from_numpy(labels).to(cuda_device)
+    _, l_fast = prototypes.build_prototypes(ft, lt, C, K, "kmeans", 7)
+    _, l_step, _ = prototypes.build_prototypes(ft, lt, C, K, "kmeans", 7, return_debug=True)
+    # K >= 4: the production path uses the cluster-paired kernel, the inspected path the inertia-reporting streaming
+    # kernel (different fp32 partial-sum segmentation), hence a tolerance instead of bit equality
+    assert torch.allclose(l_fast, l_step, rtol=2e-6, atol=1e-8)
+
+
 def test_kmeans_full_size_properties(cuda_device):
     """BASELINE config 4 size (N=100k x 2048, C=100): size-independent properties instead of an oracle run --
     counts sum to N, every assignment in range, inertia non-increasing, centroid = mean of its members."""

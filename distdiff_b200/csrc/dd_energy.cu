@@ -243,7 +243,7 @@ extern "C" int dd_energy_fwd_bwd(const float* f, const int64_t* target, const fl
     cudaStream_t st = (cudaStream_t)stream;
     if (!l) K = 0;
 #define ARGS f, target, g, l, B, D, C, K, gs, ls, normalize_f, score, per_sample, kstar, grad_f, ticket, st
-    const bool warp_map = B >= 4 * dd::sm_count() && D <= 2048;  // enough samples for >= 1 CTA of 8 warps per SM... x4
+    const bool warp_map = B >= 16 * dd::sm_count() && D <= 2048;  // a warp per sample only pays with >= 16 warps per SM in flight
     if (warp_map) {
         if (D <= 512) return dd::launch_energy<32, 4>(ARGS);
         if (D <= 1280) return dd::launch_energy<32, 10>(ARGS);

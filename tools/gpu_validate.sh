@@ -1,3 +1,4 @@
+# Full single-GPU validation: every GPU parity test, smoke(), the bench line (ours + reference arm).  TAG=... bash tools/gpu_validate.sh
 TAG=${TAG:-s5g}
 set -x
 timeout 1200 python -m pytest tests -m gpu -x -q --timeout 300 --timeout-method thread > gpurun_out/${TAG}_tests.log 2>&1; echo "tests rc=$?" >> gpurun_out/${TAG}_tests.log

@@ -155,39 +155,51 @@ __device__ __forceinline__ float affine_math(float x, float a1, float b, float c
     return y;
 }
 
-// one row (b,c) of HW elements per blockIdx.y; blockIdx.x tiles the row
-template <typename T>
+// ROWS rows (b,c) of HW elements per blockIdx.y; blockIdx.x tiles the row.  ROWS = 2 is used for 16-bit storage at large
+// batch: a 64x64 fp16 row is only 8 KB and one-row CTAs (16 KB of traffic each) do not keep enough bytes in flight.  The
+// loads are kept RAW (one uint4 per vector) until they are used, so two rows cost 8 registers per vector, not 16.
+template <typename T, int ROWS>
 __global__ void __launch_bounds__(EW_THREADS)
 affine_project_vec(const T* __restrict__ x, const float* __restrict__ a, const float* __restrict__ b,
-                   const T* __restrict__ center, T* __restrict__ y, int64_t hw_vec, int64_t HW, float radius) {
+                   const T* __restrict__ center, T* __restrict__ y, int64_t hw_vec, int64_t HW, float radius, int64_t BC) {
     using V = Vec16<T>;
     constexpr int EW_UNROLL = ew_unroll<T>();
-    const int64_t row = blockIdx.y;
-    const float a1 = __fadd_rn(1.f, a[row]);
-    const float bb = b[row];
+    const int64_t row0 = (int64_t)blockIdx.y * ROWS;
     const bool clamp = radius >= 0.f;
-    const T* xr = x + row * HW;
-    const T* cr = center ? center + row * HW : xr;
-    T* yr = y + row * HW;
+    const bool has_c = center && clamp;
     const int64_t base = (int64_t)blockIdx.x * (EW_THREADS * EW_UNROLL) + threadIdx.x;
-    V xv[EW_UNROLL], cv[EW_UNROLL];
+    uint4 xr[ROWS][EW_UNROLL], cr[ROWS][EW_UNROLL];
 #pragma unroll
-    for (int j = 0; j < EW_UNROLL; ++j) {
-        const int64_t i = base + (int64_t)j * EW_THREADS;
-        if (i < hw_vec) {
-            xv[j].load(xr + i * V::N);
-            if (center && clamp) cv[j].load(cr + i * V::N);
+    for (int r = 0; r < ROWS; ++r) {
+        const int64_t row = row0 + r;
+#pragma unroll
+        for (int j = 0; j < EW_UNROLL; ++j) {
+            const int64_t i = base + (int64_t)j * EW_THREADS;
+            if (row < BC && i < hw_vec) {
+                xr[r][j] = *reinterpret_cast<const uint4*>(x + row * HW + i * V::N);
+                if (has_c) cr[r][j] = *reinterpret_cast<const uint4*>(center + row * HW + i * V::N);
+            }
         }
     }
 #pragma unroll
-    for (int j = 0; j < EW_UNROLL; ++j) {
-        const int64_t i = base + (int64_t)j * EW_THREADS;
-        if (i < hw_vec) {
-            V o;
+    for (int r = 0; r < ROWS; ++r) {
+        const int64_t row = row0 + r;
+        if (row >= BC) continue;
+        const float a1 = __fadd_rn(1.f, a[row]);
+        const float bb = b[row];
+        T* yr = y + row * HW;
 #pragma unroll
-            for (int e = 0; e < V::N; ++e)
-                o.v[e] = affine_math(xv[j].v[e], a1, bb, (center && clamp) ? cv[j].v[e] : xv[j].v[e], radius, clamp);
-            o.store(yr + i * V::N);
+        for (int j = 0; j < EW_UNROLL; ++j) {
+            const int64_t i = base + (int64_t)j * EW_THREADS;
+            if (i < hw_vec) {
+                V xv, cv, o;
+                xv.load(reinterpret_cast<const T*>(&xr[r][j]));
+                if (has_c) cv.load(reinterpret_cast<const T*>(&cr[r][j]));
+#pragma unroll
+                for (int e = 0; e < V::N; ++e)
+                    o.v[e] = affine_math(xv.v[e], a1, bb, has_c ? cv.v[e] : xv.v[e], radius, clamp);
+                o.store(yr + i * V::N);
+            }
         }
     }
 }
@@ -358,8 +370,14 @@ static int affine_fwd_t(const void* x, const float* a, const float* b, const voi
     constexpr int EW_UNROLL = ew_unroll<T>();
     const bool vec = (HW % V::N == 0) && aligned16(x) && aligned16(center) && aligned16(y);
     if (vec) {
-        dim3 grid(vec_blocks(HW / V::N, EW_UNROLL), (unsigned)BC);
-        affine_project_vec<T><<<grid, EW_THREADS, 0, st>>>((const T*)x, a, b, (const T*)center, (T*)y, HW / V::N, HW, radius);
+        const unsigned bx = vec_blocks(HW / V::N, EW_UNROLL);
+        if (sizeof(T) == 2 && BC * bx >= 8 * 148 * 2) {   // enough rows to fill the GPU with 2-row CTAs
+            dim3 grid(bx, (unsigned)((BC + 1) / 2));
+            affine_project_vec<T, 2><<<grid, EW_THREADS, 0, st>>>((const T*)x, a, b, (const T*)center, (T*)y, HW / V::N, HW, radius, BC);
+        } else {
+            dim3 grid(bx, (unsigned)BC);
+            affine_project_vec<T, 1><<<grid, EW_THREADS, 0, st>>>((const T*)x, a, b, (const T*)center, (T*)y, HW / V::N, HW, radius, BC);
+        }
     } else {
         dim3 grid((unsigned)((HW + 255) / 256), (unsigned)BC);
         affine_project_scalar<T><<<grid, 256, 0, st>>>((const T*)x, a, b, (const T*)center, (T*)y, HW, radius);

@@ -128,6 +128,25 @@ def test_affine_project_fp32_bitexact(ops, cuda_device, shape, radius):
     assert torch.equal(y.cpu(), ref)
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("with_center", [False, True])
+def test_affine_project_large_batch_16bit(ops, cuda_device, dtype, with_center):
+    """Large 16-bit batches take the two-rows-per-CTA variant (odd row count: the last CTA has one row); it must be
+    bit-identical to the one-row variant that small batches use, and one rounding away from the fp32 result."""
+    g = torch.Generator(device=cuda_device).manual_seed(6)
+    B, Cc = 481, 5                                              # 2405 rows >= 16*148: two-row path with an odd tail
+    x = torch.randn(B, Cc, 64, 64, generator=g, device=cuda_device).to(dtype)
+    c = (x.float() + 0.3 * torch.randn(B, Cc, 64, 64, generator=g, device=cuda_device)).to(dtype) if with_center else None
+    a = torch.rand(B, Cc, 1, 1, generator=g, device=cuda_device)
+    b = torch.randn(B, Cc, 1, 1, generator=g, device=cuda_device)
+    big = ops.affine_project(x, a, b, 0.2, center=c)
+    small = torch.cat([ops.affine_project(x[i:i + 2], a[i:i + 2], b[i:i + 2], 0.2, center=None if c is None else c[i:i + 2])
+                       for i in range(0, B, 2)])
+    assert torch.equal(big, small)
+    ref32 = ops.affine_project(x.float(), a, b, 0.2, center=None if c is None else c.float())
+    assert torch.equal(big, ref32.to(dtype))
+
+
 def test_linfball_golden(ops, cuda_device, golden):
     c = golden["linfball"]
     B, Cc = c["t"].shape[:2]

@@ -302,7 +302,12 @@ def extract_prototypes_with_encoder(args, model, trainset_factory: Optional[Call
     from torchvision import transforms
     path = prototype_path(args)
     method = getattr(args, "cluster_method", "agglomerative")
-    if cache and method == "agglomerative" and os.path.exists(path):
+    have = cache and method == "agglomerative" and os.path.exists(path)
+    if coll is not None and coll.world > 1:          # one decision for all ranks: the stage below is collective
+        box = [bool(have)]
+        coll.dist.broadcast_object_list(box, src=0)
+        have = box[0]
+    if have:
         z = np.load(path)
         return z["global_prototypes"], z["local_prototypes"]
     transform = transforms.Compose([                                            # dataloader.py:736-742

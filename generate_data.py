@@ -113,6 +113,18 @@ def main(args):
         raise RuntimeError("generate_data.py needs a CUDA device: the guidance hot path has no CPU fallback")
     device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
     torch.cuda.set_device(device)
+    # Launched by torchrun (one process per GPU): rank r IS the reference's `--split r --total_split P` process
+    # (scripts/exps/expand_diff.sh starts those by hand), and the prototype stage is sharded over the ranks -- features
+    # of 1/P of the images per GPU, class sums over NCCL, k-means centroids through the fused NVLink peer exchange --
+    # instead of every process recomputing all of it (generate_data.py:1104).
+    world, rank = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0))
+    coll = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+        coll = prototypes.PeerCollective()
+        args.split, args.total_split = rank, world
+        logging.getLogger("distdiff_b200").info("torchrun: rank %d of %d -> --split %d --total_split %d", rank, world, rank, world)
     if args.seed is not None:
         expand.set_seed(args.seed)                                                                          # :860-861
     weight_dtype = {"fp16": torch.float16, "bf16": torch.bfloat16, "fp32": torch.float32}[args.dtype]       # :1039
@@ -128,7 +140,7 @@ def main(args):
 
     # prototypes (:1100-1127) -- guide in fp32 for extraction (dataloader.py:745), then cast (:1106)
     args.num_classes = len(dataset.class_names)
-    global_np, local_np = prototypes.extract_prototypes_with_encoder(args, image_encoder)
+    global_np, local_np = prototypes.extract_prototypes_with_encoder(args, image_encoder, coll=coll)
     if args.optimize_targets is not None:
         args.optimize_targets = args.optimize_targets.split("-")                                            # :1109
     print(f"optimize strategy: {args.guidance_type}, target: {args.optimize_targets}, learning rate: {args.rho}")
@@ -144,6 +156,14 @@ def main(args):
         loader = list(itertools.islice(iter(loader), args.max_batches))
     n = expand.run_expansion(args, ex, loader, save=True)
     print(f"expanded {n} images into {args.output_dir}")
+    if coll is not None:
+        import torch.distributed as dist
+        tot = torch.tensor([n], device=device)
+        dist.all_reduce(tot)                     # also the final barrier: every rank's files are on disk
+        if rank == 0:
+            print(f"all {world} ranks: expanded {int(tot)} images")
+        coll.close()
+        dist.destroy_process_group()
     return n
 
 

@@ -347,7 +347,7 @@ def run_ours(opt):
         e2e = world * opt.batch * opt.steps / t_e2e
         line = {"metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": world, "steps": opt.steps, "warmup": opt.warmup,
                 "ms_per_step": round(1e3 * t_res / opt.steps, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32 arithmetic in the guidance kernels; " + opt.dtype + " latent/UNet/VAE storage (reference: fp16)",
+                "dtype": "f32",   # arithmetic type of the guidance kernels; the latent / UNet / VAE storage type is config.storage_dtype
                 "data": "synthetic", "config": workload_config(a, opt.batch, world, not opt.no_cuda_graph, opt.dtype, not opt.no_channels_last),
                 "e2e": {"value": round(e2e, 4), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": round(1e3 * t_e2e / opt.steps, 2)},

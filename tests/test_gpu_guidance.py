@@ -222,3 +222,31 @@ def test_kmeans_full_size_properties(cuda_device):
     # class means of unit rows: ||mean|| <= 1, and equal to a torch reference
     ref = torch.zeros(C, D, dtype=torch.float64, device=cuda_device).index_add_(0, labels, torch.nn.functional.normalize(feats, dim=-1).double()) / (N // C)
     assert torch.allclose(gm.double(), ref, rtol=1e-5, atol=1e-8)
+
+
+def test_peer_exchange_single_rank_process_group(cuda_device):
+    """The fused peer-memory exchange (csrc/dd_peer.cu) with a 1-rank NCCL process group on one GPU: arena creation, IPC
+    export, flag barriers (self-signalled), reduce + update + publish, and the C Lloyd loop -- must reproduce the plain
+    single-GPU path bit for bit (the multi-GPU comparison against NCCL is tools/dist_check.py)."""
+    import socket
+    import torch.distributed as dist
+    from distdiff_b200 import prototypes
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1, device_id=cuda_device)
+    try:
+        coll = prototypes.PeerCollective()
+        rng = np.random.default_rng(5)
+        C, K, D, per = 7, 4, 512, 90
+        centers = rng.normal(size=(C, K, D)) * 4.0
+        labels = np.repeat(np.arange(C), per); rng.shuffle(labels)
+        feats = (centers[labels, rng.integers(0, K, size=len(labels))] + rng.normal(size=(len(labels), D))).astype(np.float32)
+        ft, lt = torch.from_numpy(feats).to(cuda_device), torch.from_numpy(labels).to(cuda_device)
+        for Kk in (3, 4):
+            g0, l0 = prototypes.build_prototypes(ft, lt, C, Kk, "kmeans", 6)
+            g1, l1 = prototypes.build_prototypes(ft, lt, C, Kk, "kmeans", 6, coll=coll)
+            assert torch.equal(g0, g1) and torch.equal(l0, l1)
+            _, l2, dbg = prototypes.build_prototypes(ft, lt, C, Kk, "kmeans", 6, coll=coll, return_debug=True)
+            assert int(dbg["counts"].sum()) == len(labels) and torch.allclose(l2, l1, rtol=2e-6, atol=1e-8)
+        coll.close()
+    finally:
+        dist.destroy_process_group()

@@ -1,4 +1,4 @@
-"""CPU, world_size 2 over `gloo`: the N>1 host logic of the path.
+"""CPU, world_size 2 (and 3: ragged shards) over `gloo`: the N>1 host logic of the path.
 
 The CUDA kernels cannot run here, so `distdiff_b200.prototypes.ops` is swapped for oracle-backed CPU stand-ins
 (tests/cpu_kernels.py) inside the worker processes; everything ABOVE the kernels is the product code under test:
@@ -84,10 +84,9 @@ def _worker(rank, world, port, method, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("method", ["kmeans", "agglomerative"])
-def test_sharded_prototypes_world2_gloo(tmp_path, method):
+@pytest.mark.parametrize("method,world", [("kmeans", 2), ("agglomerative", 2), ("kmeans", 3)])
+def test_sharded_prototypes_gloo(tmp_path, method, world):
     from oracle import prototypes as o_proto
-    world = 2
     mp.spawn(_worker, args=(world, _free_port(), method, str(tmp_path)), nprocs=world, join=True)
     feats, labels, C, K = _data()
     fn = o_proto.l2_normalize_rows(feats)
@@ -99,7 +98,8 @@ def test_sharded_prototypes_world2_gloo(tmp_path, method):
     for r in range(world):                                         # every rank ends with the same, full result
         np.testing.assert_allclose(outs[r]["g"], g_ref, rtol=1e-6, atol=1e-7)
         np.testing.assert_allclose(outs[r]["l"], l_ref, rtol=1e-6, atol=1e-7)
-    np.testing.assert_array_equal(outs[0]["l"], outs[1]["l"])
+    for r in range(1, world):
+        np.testing.assert_array_equal(outs[0]["l"], outs[r]["l"])
     if method == "kmeans":                                         # assignments of the shards, concatenated, == unsharded
         assign = np.concatenate([o["assign"] for o in outs])
         ref = np.empty(len(labels), dtype=np.int32)

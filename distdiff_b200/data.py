@@ -86,7 +86,11 @@ class SDDataset(data.Dataset):
     """dataloader.py:750-852: per item the cached VAE latent, the class prompt embedding and the unconditional
     embedding (stored under the reference's key names), the label, class name and image path."""
 
-    def __init__(self, args, text_embed_fn, vae, size=512, device="cuda", latent_dtype=torch.float32):
+    def __init__(self, args, text_embed_fn, vae, size=512, device="cuda", latent_dtype=torch.float32, only=None):
+        """``only``: indices this process will read (its ``--split`` block).  Used only with ``args.shard_latents``:
+        the VAE encode then covers just those images, each with its own generator seeded by (seed, index), so the
+        latents do not depend on how the set is split -- but they are NOT the reference's draws (the reference encodes
+        the whole set in every process from one sequential RNG stream, dataloader.py:798-811), hence opt-in."""
         from torchvision import transforms
         self.args = args
         self.base = load_trainset(args, None)
@@ -98,7 +102,10 @@ class SDDataset(data.Dataset):
                                       transforms.ToTensor(), transforms.Normalize([0.5], [0.5])])
         self.prompt_embeds = [text_embed_fn(PROMPT_TEMPLATE.format(n)) for n in self.class_names]
         self.uncond_embeds = text_embed_fn("")
-        self.image_latents = self._latents(vae, device, latent_dtype)
+        if getattr(args, "shard_latents", False):
+            self.image_latents = self._latents_sharded(vae, device, latent_dtype, range(len(self.base)) if only is None else only)
+        else:
+            self.image_latents = self._latents(vae, device, latent_dtype)
 
     def _cache_path(self):
         model_id = str(getattr(self.args, "pretrained_model_name_or_path", "random-init")).replace("/", "--")
@@ -122,11 +129,38 @@ class SDDataset(data.Dataset):
             os.replace(tmp, path)
         return out
 
+    @torch.no_grad()
+    def _latents_sharded(self, vae, device, dtype, indices) -> List[Optional[torch.Tensor]]:
+        """Encode only ``indices`` (no P-fold redundant encode under --total_split P).  Crop position
+        and posterior noise of image j come from generators seeded by (seed, j): split-invariant by construction."""
+        out: List[Optional[torch.Tensor]] = [None] * len(self.base)
+        seed = int(getattr(self.args, "seed", 0) or 0)
+        idx = [int(j) for j in indices]
+        bs = 16
+        wdt = next(vae.parameters()).dtype
+        for i in range(0, len(idx), bs):
+            chunk = idx[i:i + bs]
+            imgs = []
+            for j in chunk:
+                state = torch.random.get_rng_state()
+                torch.manual_seed(seed * 1_000_003 + j)                       # RandomCrop draws from the global CPU generator
+                imgs.append(self.tf(self.base.image(j)))
+                torch.random.set_rng_state(state)
+            moments = vae.encode(torch.stack(imgs).to(device, wdt)).latent_dist
+            for k, j in enumerate(chunk):
+                g = torch.Generator(device="cpu").manual_seed(seed * 1_000_003 + 7919 + j)
+                noise = torch.randn(moments.mean[k].shape, generator=g).to(device, moments.mean.dtype)
+                z = (moments.mean[k] + moments.std[k] * noise) * vae.config.scaling_factor
+                out[j] = z[None].to("cpu", dtype)
+        return out
+
     def __len__(self):
         return len(self.base)
 
     def __getitem__(self, idx):
         y = self.base.targets[idx]
+        if self.image_latents[idx] is None:
+            raise IndexError(f"image {idx} is outside the block this process encoded (--shard_latents)")
         return {"image_latents": self.image_latents[idx], "instance_prompt_ids": self.prompt_embeds[y],
                 "uncond_inputs_ids": self.uncond_embeds, "targets": y, "class_names": self.class_names[y],
                 "image_paths": self.base.paths[idx]}

@@ -70,6 +70,8 @@ def parse_args(input_args=None):
     p.add_argument("--synthetic_per_class", type=int, default=30)
     p.add_argument("--cuda_graph", action="store_true", help="replay the unguided step (UNet + K5) from a CUDA graph")
     p.add_argument("--cache_latents", action="store_true", help="persist save/vae_embedding/.../image_latents.pt like the reference")
+    p.add_argument("--shard_latents", action="store_true",
+                   help="VAE-encode only this split's images, with per-image generators (split-invariant, but not the reference's RNG draws)")
     p.add_argument("--tiny_models", action="store_true", help="tiny random-init UNet/VAE/guide (tests)")
     p.add_argument("--max_batches", type=int, default=None, help="stop after this many batches (smoke runs)")
     args, unknown = p.parse_known_args(input_args)
@@ -133,7 +135,10 @@ def main(args):
 
     # dataset + latents (VAE encode in fp32 like the reference, :983), then the --split block (:1001-1009)
     embed = dd_data.random_text_embedder()
-    dataset = dd_data.SDDataset(args, embed, vae, size=512 if not args.tiny_models else 64, device=device)
+    only = None
+    if args.shard_latents:      # opt-in: encode only this process's block (per-image generators; not the reference's draws)
+        only = guidance.split_mask(len(dd_data.load_trainset(args, None)), args.split, args.total_split)
+    dataset = dd_data.SDDataset(args, embed, vae, size=512 if not args.tiny_models else 64, device=device, only=only)
     mask = guidance.split_mask(len(dataset), args.split, args.total_split)
     loader = DataLoader(Subset(dataset, mask), batch_size=args.train_batch_size, shuffle=False,
                         collate_fn=dd_data.collate_fn, num_workers=args.dataloader_num_workers, drop_last=False)

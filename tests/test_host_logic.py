@@ -113,6 +113,34 @@ def test_latent_cache_layout_and_collate(tmp_path, monkeypatch):
     assert torch.equal(embed("a photo of a class 000."), ds[0]["instance_prompt_ids"])   # dataloader.py:52-62 template
 
 
+def test_sharded_latents_are_split_invariant(tmp_path, monkeypatch):
+    """--shard_latents: each split encodes only its block, with per-image generators, so the union of
+    the splits equals the unsplit run and images outside the block are refused."""
+    from distdiff_b200 import data, guidance, nets
+    monkeypatch.chdir(tmp_path)
+    torch.manual_seed(0)
+    vae = nets.AutoencoderKL(chs=(32, 32, 64, 64)).eval()
+    args = types.SimpleNamespace(dataset="caltech-101", data_root="nowhere", synthetic_classes=3, synthetic_per_class=3, seed=42,
+                                 pretrained_model_name_or_path="x", cache_latents=False, center_crop=False, shard_latents=True)
+    embed = data.random_text_embedder()
+    full = data.SDDataset(args, embed, vae, size=32, device="cpu")
+    assert all(t is not None and t.shape == (1, 4, 4, 4) for t in full.image_latents)
+    torch.manual_seed(123)                                                      # the global RNG state must not matter
+    for split in range(2):
+        mask = guidance.split_mask(len(full), split, 2)
+        part = data.SDDataset(args, embed, vae, size=32, device="cpu", only=mask)
+        for j in range(len(full)):
+            if j in mask:
+                assert torch.allclose(part.image_latents[j], full.image_latents[j], rtol=1e-5, atol=1e-6)
+            else:
+                assert part.image_latents[j] is None
+                with pytest.raises(IndexError):
+                    part[j]
+    args.seed = 43                                                              # a different --seed gives different draws
+    other = data.SDDataset(args, embed, vae, size=32, device="cpu", only=[0])
+    assert not torch.allclose(other.image_latents[0], full.image_latents[0])
+
+
 def test_output_path_layout():
     from distdiff_b200 import expand
     args = types.SimpleNamespace(output_dir="data_expand")
@@ -128,7 +156,7 @@ def test_cli_surface_matches_reference_flags():
     # reference defaults (generate_data.py:167-453)
     assert (a.total_split, a.split, a.num_images_per_prompt, a.K, a.guidance_scale, a.seed, a.train_batch_size) == (8, 0, 4, 3, 7.5, 42, 2)
     assert (a.strength, a.rho, a.gs, a.ls, a.constraint_value, a.guidance_step, a.guidance_period) == (0.9, 10.0, 1.0, 1.0, 0.8, 1, 1)
-    assert a.guidance_type is None and a.cluster_method == "agglomerative"
+    assert a.guidance_type is None and a.cluster_method == "agglomerative" and a.shard_latents is False
     b = gd.parse_args(["--guidance_type", "transform_guidance", "--optimize_targets", "global_prototype-local_prototype", "--K", "5",
                        "--report_to", "wandb", "--some_training_only_flag"])     # flags off the expansion path are ignored, not fatal
     assert b.guidance_type == "transform_guidance" and b.K == 5 and b.optimize_targets == "global_prototype-local_prototype"

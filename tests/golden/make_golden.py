@@ -50,7 +50,7 @@ def extract_functions(path, names, namespace):
     return found
 
 
-def main():
+def main(out_path=None):
     torch.Tensor.cuda = lambda self, *a, **k: self          # reference hard-codes .cuda()
     torch.nn.Module.cuda = lambda self, *a, **k: self
     torch.cuda.empty_cache = lambda: None
@@ -152,10 +152,10 @@ def main():
                                     global_prototypes=torch.from_numpy(np.asarray(gl, dtype=np.float32)),
                                     local_prototypes=torch.from_numpy(np.asarray(lc, dtype=np.float32)))
 
-    path = os.path.join(HERE, "reference_golden.pt")
+    path = out_path or os.path.join(HERE, "reference_golden.pt")
     torch.save(out, path)
     print("wrote", path, os.path.getsize(path), "bytes; reference line spans:", lines)
 
 
 if __name__ == "__main__":
-    main()
+    main(sys.argv[1] if len(sys.argv) > 1 else None)   # optional output path (tests regenerate into a temp file)

@@ -1,6 +1,7 @@
 """CPU: the oracle restatement against the reference's own outputs (tests/golden/reference_golden.pt,
 made by tests/golden/make_golden.py from the reference function bodies) and against closed-form
 identities / known values of the restated DDIM scheduler."""
+import os
 import types
 
 import numpy as np
@@ -231,3 +232,37 @@ def test_decode_to_uint8_matches_save_image_array():
     buf = io.BytesIO()
     save_image([o_img.denormalize(x)[0]], buf, format="png")
     assert np.array_equal(np.asarray(Image.open(io.BytesIO(buf.getvalue()))), o_img.decode_to_uint8(x)[0])
+
+
+def test_committed_golden_regenerates_from_the_reference(tmp_path, golden):
+    """Only where /root/reference exists (the build container): re-run tests/golden/make_golden.py -- the reference's own
+    function bodies, pulled out of its sources with `ast` -- and compare with the committed fixture, so the fixture cannot
+    drift from the reference or from the script that claims to have made it."""
+    import subprocess
+    import sys
+    if not os.path.isdir("/root/reference"):
+        pytest.skip("the reference tree is only mounted in the build container")
+    out = str(tmp_path / "regen.pt")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "golden", "make_golden.py"), out], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    new = torch.load(out, weights_only=False)
+    assert new["reference_lines"] == golden["reference_lines"]
+
+    def same(a, b, path):
+        if isinstance(a, dict):
+            assert a.keys() == b.keys(), path
+            for k in a:
+                same(a[k], b[k], f"{path}/{k}")
+        elif torch.is_tensor(a):
+            assert a.shape == b.shape and torch.allclose(a.double(), b.double(), rtol=1e-5, atol=1e-6), path
+        elif isinstance(a, float):
+            assert abs(a - b) <= 1e-5 * max(1.0, abs(b)), path
+        elif isinstance(a, (list, tuple)) and a and torch.is_tensor(a[0]):
+            for i, (x, y) in enumerate(zip(a, b)):
+                same(x, y, f"{path}[{i}]")
+        else:
+            assert a == b or path.endswith("torch_version"), path
+    for key in golden:
+        if key != "torch_version":
+            same(new[key], golden[key], key)

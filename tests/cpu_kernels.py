@@ -79,7 +79,6 @@ def agglo_average(x_sorted, class_off, K, max_class_size):
     labels = torch.full((N,), -1, dtype=torch.int32)
     s = torch.zeros(Cn, K, D, dtype=torch.float64)
     n = torch.zeros(Cn, K, dtype=torch.int64)
-    base = int(class_off[0])
     for c in range(Cn):
         a, b = int(class_off[c]), int(class_off[c + 1])
         Xc = x_sorted[a:b].numpy()
@@ -87,5 +86,4 @@ def agglo_average(x_sorted, class_off, K, max_class_size):
         ss, nn = o_proto.kmeans_sums(Xc, lab, K)
         labels[a:b] = torch.from_numpy(lab)
         s[c] = torch.from_numpy(ss); n[c] = torch.from_numpy(nn)
-    del base
     return labels, s, n, torch.zeros(Cn, dtype=torch.int32)

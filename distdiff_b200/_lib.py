@@ -32,7 +32,8 @@ SIGNATURES = {
     "dd_bicubic_resize_fwd": (_i, [_p, _l, _i, _i, _i, _i, _i, _p, _p]),
     "dd_bicubic_resize_bwd": (_i, [_p, _l, _i, _i, _i, _i, _i, _p, _p]),
     "dd_image_to_uint8": (_i, [_p, _l, _i, _i, _i, _i, _i, _p, _p]),
-    "dd_energy_fwd_bwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _f, _f, _i, _p, _p, _p, _p, _p, _p]),
+    "dd_energy_workspace_bytes": (_z, [_i, _i]),
+    "dd_energy_fwd_bwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _f, _f, _i, _p, _p, _p, _p, _p, _z, _i, _p]),
     "dd_proto_workspace_bytes": (_z, [_i, _i, _i]),
     "dd_rownorm_classsum": (_i, [_p, _p, _p, _l, _i, _i, _p, _p, _p, _p, _z, _p]),
     "dd_class_mean": (_i, [_p, _p, _l, _i, _p, _p, _p]),

@@ -7,10 +7,20 @@
 // hop when a whole CTA works on a sample), picks k* = argmax <f, l_k> (first max on ties), and writes
 // d score / d f_b.  The batch mean is finished deterministically by the last CTA to arrive (ticket).
 //
-// Two mappings, same code: GROUP = 32 (one warp per sample, 8 samples per CTA; used when B is large enough
-// to fill the GPU) and GROUP = 256 (one CTA per sample; the reference's B = 1..16, latency matters).
-// HBM roofline: compulsory traffic is f (read) + grad_f (write) = 2*D*4 bytes per sample.
+// Two kernels:
+//   * energy_kernel: one CTA per sample (the reference's B = 1..16 and everything up to a few thousand samples,
+//     where latency matters): prototypes come straight from L2.
+//   * energy_tile_kernel (large B): the prototype reads of the per-sample kernel are (K+3) rows of L2->SM traffic
+//     per sample against 2 rows of HBM traffic, i.e. L2-bound at ~0.25-0.36 of the HBM roofline.  The tile kernel
+//     removes them: samples are bucketed by class (a counting sort in two tiny kernels), persistent CTAs walk
+//     contiguous runs of the class-sorted order, every thread OWNS 8 columns of D and keeps the class's K+1
+//     prototype slices in registers across the run, sample rows are gathered by the TMA engine (one
+//     cp.async.bulk per row through the permutation) into a shared-memory ring, and the per-sample sums
+//     (K dots [+ |f|^2], then 4 distance / Jacobian sums) are reduced by transposed warp shuffles + one
+//     shared-memory hop.  Per sample the SM then moves f once from HBM and grad once to HBM and nothing else.
+// HBM roofline: compulsory traffic is f (read) + grad_f (write) = 2*D*4 bytes per sample (+ the tables once).
 #include "dd_common.cuh"
+#include "dd_stream.cuh"
 
 namespace dd {
 
@@ -41,7 +51,7 @@ __device__ __forceinline__ void group_sum(float (&v)[NV], float* red /* [NV][8] 
 
 // CH = float4 chunks of the row held per thread (D <= CH * 4 * GROUP)
 template <int GROUP, int CH, int KMAX>
-__global__ void __launch_bounds__(EN_THREADS, GROUP == 32 ? 2 : 1)
+__global__ void __launch_bounds__(EN_THREADS, CH <= 2 ? 3 : 1)
 energy_kernel(const float* __restrict__ f, const int64_t* __restrict__ target, const float* __restrict__ g,
               const float* __restrict__ l, int B, int D, int C, int K, float gs, float ls, int normalize_f,
               float* __restrict__ score, float* __restrict__ per_sample, int32_t* __restrict__ kstar_out,
@@ -209,47 +219,534 @@ energy_kernel(const float* __restrict__ f, const int64_t* __restrict__ target, c
     }
 }
 
-template <int GROUP, int CH>
+// ---------------------------------------------------------------------------------------------------
+// class bucketing for the tile kernel: rank inside the class (warp-aggregated atomics), exclusive scan of the
+// class counts by the last CTA, then a scatter.  Bucket C collects out-of-range targets (poisoned with NaN).
+// The order inside a bucket is arbitrary; every output is written at the sample's ORIGINAL index and the batch
+// mean is taken in index order, so results do not depend on it.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(EN_THREADS)
+class_rank_kernel(const int64_t* __restrict__ target, int B, int C, int* __restrict__ counts /* [C+1], zero */,
+                  int* __restrict__ rank /* [B] */, int* __restrict__ off /* [C+2] */, unsigned int* __restrict__ ticket) {
+    __shared__ int wsum[EN_THREADS / 32];
+    __shared__ bool is_last;
+    const int b = blockIdx.x * EN_THREADS + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const unsigned act = __ballot_sync(0xffffffffu, b < B);
+    if (b < B) {
+        const int64_t y = target[b];
+        const int c = (y >= 0 && y < C) ? (int)y : C;
+        const unsigned m = __match_any_sync(act, c);
+        const int leader = __ffs(m) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(counts + c, __popc(m));
+        base = __shfl_sync(m, base, leader);
+        rank[b] = base + __popc(m & ((1u << lane) - 1u));
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    // exclusive scan of counts[0..C] -> off[0..C+1]; thread t owns a contiguous chunk
+    const int n = C + 1;
+    const int per = (n + EN_THREADS - 1) / EN_THREADS;
+    const int lo = threadIdx.x * per, hi = min(lo + per, n);
+    int s = 0;
+    for (int i = lo; i < hi; ++i) s += __ldcg(counts + i);
+    int incl = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) wsum[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    int wbase = 0;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) wbase += wsum[w];
+    int run = wbase + incl - s;
+    for (int i = lo; i < hi; ++i) { off[i] = run; run += __ldcg(counts + i); }
+    if (threadIdx.x == 0) off[n] = B;
+}
+
+__global__ void __launch_bounds__(EN_THREADS)
+class_scatter_kernel(const int64_t* __restrict__ target, int B, int C, const int* __restrict__ rank,
+                     const int* __restrict__ off, int* __restrict__ perm) {
+    const int b = blockIdx.x * EN_THREADS + threadIdx.x;
+    if (b >= B) return;
+    const int64_t y = target[b];
+    const int c = (y >= 0 && y < C) ? (int)y : C;
+    perm[off[c] + rank[b]] = b;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// large B: class-sorted tile kernel
+// ---------------------------------------------------------------------------------------------------
+constexpr int ET_R = 4;  // samples per batch (one ring stage)
+
+// Warp sum of S packed (float2) partials per lane through a warp-private shared-memory transposition: every lane
+// stores its S partials (STS.64 into tr[slot][lane]); LPS = 32 / pow2(S) lanes then share a slot row, each adds its
+// interleaved quarter of the 32 partials (LDS.128 + packed adds, fixed order) and LPS-1 shuffle steps finish.  Costs
+// ~S + 16/LPS + 32/LPS instructions against ~8 S for the shuffle butterfly.  All LPS lanes of slot (lane / LPS)
+// return its total; the row stride keeps the LDS.128 of a quarter-warp on distinct banks.
+template <int S>
+struct TrCfg {
+    static constexpr int P = pow2_ge(S) < 8 ? 8 : pow2_ge(S);
+    static constexpr int LPS = 32 / P;                                     // 1, 2 or 4
+    static constexpr int STRIDE = LPS == 1 ? 34 : (LPS == 2 ? 36 : 40);    // float2 per slot row
+    static constexpr int FLOAT2S = S * STRIDE;
+};
+template <int S>
+__device__ __forceinline__ float2 tr_reduce(const float2 (&v)[S], float2* tr, int lane) {
+    using Cfg = TrCfg<S>;
+    static_assert(S >= 1 && S <= 32, "at most 32 slots per round");
+#pragma unroll
+    for (int i = 0; i < S; ++i) tr[i * Cfg::STRIDE + lane] = v[i];
+    __syncwarp();
+    const int slot = lane / Cfg::LPS, part = lane % Cfg::LPS;
+    const float4* row = reinterpret_cast<const float4*>(tr + (slot < S ? slot : 0) * Cfg::STRIDE);
+    constexpr int NF4 = 16 / Cfg::LPS;
+    float2 c0 = make_float2(0.f, 0.f), c1 = c0;
+#pragma unroll
+    for (int i = 0; i < NF4; ++i) {
+        const float4 u = row[i * Cfg::LPS + part];
+        c0 = fadd2(c0, make_float2(u.x, u.y));
+        c1 = fadd2(c1, make_float2(u.z, u.w));
+    }
+    float2 t = fadd2(c0, c1);
+#pragma unroll
+    for (int o = Cfg::LPS / 2; o > 0; o >>= 1) {
+        t.x += __shfl_xor_sync(0xffffffffu, t.x, o);
+        t.y += __shfl_xor_sync(0xffffffffu, t.y, o);
+    }
+    __syncwarp();   // the buffer may be overwritten by the next round
+    return t;
+}
+
+template <int KT>
+struct TileCfg {
+    static constexpr int R = ET_R;
+    static constexpr int SP1 = (KT + 2) / 2;                 // packed slots per row in pass 1: K dots + |f|^2
+    static constexpr int RS = (32 / SP1) >= R ? R : (32 / SP1);   // rows per reduction round
+    static constexpr int NSUB = (R + RS - 1) / RS;
+    static constexpr int S1 = RS * SP1;                      // slots per round
+    static constexpr int S2 = R * 2;                         // pass 2: (|fn-g|^2, |fn-l*|^2), (<f,g-fn>, <f,l*-fn>) per row
+    static constexpr int TR_FLOAT2S = TrCfg<S1>::FLOAT2S > TrCfg<S2>::FLOAT2S ? TrCfg<S1>::FLOAT2S : TrCfg<S2>::FLOAT2S;
+    static constexpr int CTAS_PER_SM = KT <= 5 ? 2 : 1;
+    static constexpr size_t SMEM_FIXED = PK_MAX_STAGES * sizeof(uint64_t) + (size_t)PK_WARPS * TR_FLOAT2S * sizeof(float2) +
+                                         (size_t)PK_WARPS * (NSUB + 1) * 32 * sizeof(float2);
+};
+
+// run body(p) with p = the K-th prototype slice, K CTA-uniform: a tree of uniform branches around COPIES of the body,
+// so the selected registers are used in place (a register array cannot be indexed at run time without going through
+// local memory, and copying 8 registers per selection costs as much as the arithmetic that follows)
+template <int KT, int LO, int HI, typename F>
+__device__ __forceinline__ void with_proto(const float4 (&l8)[KT][PK_CH], int k, F&& body) {
+    if constexpr (HI - LO == 1) {
+        body(l8[LO]);
+    } else {
+        constexpr int MID = (LO + HI) / 2;
+        if (k < MID) with_proto<KT, LO, MID>(l8, k, body);
+        else with_proto<KT, MID, HI>(l8, k, body);
+    }
+}
+
+__device__ __forceinline__ float2 lo2(const float4& v) { return make_float2(v.x, v.y); }
+__device__ __forceinline__ float2 hi2(const float4& v) { return make_float2(v.z, v.w); }
+
+// FULL: D == 2048 (every thread owns both of its chunks), K == KT, both prototype tables present -> no predicates
+template <int KT, bool FULL>
+__global__ void __launch_bounds__(EN_THREADS, TileCfg<KT>::CTAS_PER_SM)
+energy_tile_kernel(const float* __restrict__ f, const int* __restrict__ perm, const int* __restrict__ off,
+                   const float* __restrict__ g, const float* __restrict__ l, int B, int D_, int C, int K_, float gs, float ls,
+                   int normalize_f, float* __restrict__ score, float* __restrict__ per_sample, int32_t* __restrict__ kstar_out,
+                   float* __restrict__ grad_f, unsigned int* __restrict__ ticket, int stages) {
+    using Cfg = TileCfg<KT>;
+    constexpr int R = Cfg::R, SP1 = Cfg::SP1, RS = Cfg::RS, NSUB = Cfg::NSUB, S1 = Cfg::S1, S2 = Cfg::S2;
+    static_assert(SP1 <= 32, "KT too large");
+    const int D = FULL ? PK_MAX_D : D_;
+    const int K = FULL ? KT : K_;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int stage_elems = R * D;
+    float* ring = reinterpret_cast<float*>(smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)stages * stage_elems * sizeof(float));
+    float2* tr_all = reinterpret_cast<float2*>(full + PK_MAX_STAGES);          // [PK_WARPS][TR_FLOAT2S]
+    float2* cross1 = tr_all + PK_WARPS * Cfg::TR_FLOAT2S;                     // [PK_WARPS][NSUB][32]
+    float2* cross2 = cross1 + PK_WARPS * NSUB * 32;                           // [PK_WARPS][32]
+    __shared__ float fin[EN_THREADS];
+    __shared__ bool is_last;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    float2* tr = tr_all + warp * Cfg::TR_FLOAT2S;
+    const int G = gridDim.x, gi = blockIdx.x;
+    const int r0 = (int)((int64_t)B * gi / G), r1 = (int)((int64_t)B * (gi + 1) / G);
+    const int nch = D >> 2;
+    int chunk[PK_CH];
+    bool own[PK_CH];
+#pragma unroll
+    for (int ch = 0; ch < PK_CH; ++ch) { chunk[ch] = tid + ch * PK_THREADS; own[ch] = FULL || chunk[ch] < nch; }
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool has_g = FULL || g != nullptr, has_l = FULL || l != nullptr;
+    const float invB = 1.f / (float)B;
+
+    if (tid == 0) {
+        for (int s = 0; s < stages; ++s) mbar_init(&full[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    // walk over the class-sorted positions [r0, r1) in batches of <= R rows of one class (32-bit cursors)
+    auto take = [&](int& row, int& c, int& end, int& b_row, int& b_n, int& b_c) {
+        while (end <= row) { ++c; end = __ldg(off + c + 1); }
+        int n = end - row;
+        if (n > R) n = R;
+        if (n > r1 - row) n = r1 - row;
+        b_row = row; b_n = n; b_c = c;
+        row += n;
+    };
+    auto issue = [&](int s, int br, int bn) {   // gather bn sample rows through the class-sort permutation
+        const uint32_t row_bytes = (uint32_t)D * sizeof(float);
+        mbar_expect_tx(&full[s], row_bytes * bn);
+        for (int i = 0; i < bn; ++i)
+            bulk_g2s(ring + s * stage_elems + i * D, f + (int64_t)__ldg(perm + br + i) * D, row_bytes, &full[s]);
+    };
+
+    int irow = r0, crow = r0;
+    int ic = (r0 < r1) ? find_class(off, C + 1, r0) : 0;
+    int cc = ic;
+    int iend = (r0 < r1) ? __ldg(off + ic + 1) : 0, cend = iend;
+    if (tid == 0) {
+        for (int s = 0; s < stages && irow < r1; ++s) {
+            int br, bn, bc;
+            take(irow, ic, iend, br, bn, bc);
+            issue(s, br, bn);
+        }
+    }
+
+    float4 g8[PK_CH], l8[KT][PK_CH];
+    int cur = -1;
+    int s = 0;
+    uint32_t parity = 0;
+    while (crow < r1) {
+        int brow, bn, bc;
+        take(crow, cc, cend, brow, bn, bc);
+        const bool valid = bc < C;   // bucket C = out-of-range targets
+        if (bc != cur && valid) {
+            cur = bc;
+#pragma unroll
+            for (int ch = 0; ch < PK_CH; ++ch) {
+                g8[ch] = (has_g && own[ch]) ? __ldg(reinterpret_cast<const float4*>(g + (int64_t)bc * D) + chunk[ch]) : zero4;
+#pragma unroll
+                for (int k = 0; k < KT; ++k)
+                    l8[k][ch] = (has_l && (FULL || k < K) && own[ch])
+                                    ? __ldg(reinterpret_cast<const float4*>(l + ((int64_t)bc * K + k) * D) + chunk[ch]) : zero4;
+            }
+        }
+        const int orig_l = lane < bn ? __ldg(perm + brow + lane) : 0;   // lane r: original index of row r
+        mbar_wait(&full[s], parity);
+        const float* st = ring + s * stage_elems;
+        float4 xv[R][PK_CH];
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int ch = 0; ch < PK_CH; ++ch) {
+                if (FULL) xv[r][ch] = *reinterpret_cast<const float4*>(st + r * PK_MAX_D + chunk[ch] * 4);
+                else xv[r][ch] = own[ch] ? *reinterpret_cast<const float4*>(st + r * D + chunk[ch] * 4) : zero4;
+            }
+
+        // ---- pass 1: K dots with the raw row + |f|^2, packed in pairs, RS rows per transposition round ----
+#pragma unroll
+        for (int h = 0; h < NSUB; ++h) {
+            float2 v[S1];
+#pragma unroll
+            for (int rr = 0; rr < RS; ++rr) {
+                const int r = h * RS + rr;
+                float d[2 * SP1];
+#pragma unroll
+                for (int j = 0; j < 2 * SP1; ++j) d[j] = 0.f;
+                if (r < R) {
+#pragma unroll
+                    for (int k = 0; k < KT; ++k) {
+                        if (FULL || k < K) {
+                            float2 a = fmul2(lo2(xv[r][0]), lo2(l8[k][0]));
+                            a = ffma2(hi2(xv[r][0]), hi2(l8[k][0]), a);
+#pragma unroll
+                            for (int ch = 1; ch < PK_CH; ++ch) a = dot4(xv[r][ch], l8[k][ch], a);
+                            d[k] = a.x + a.y;
+                        }
+                    }
+                    if (normalize_f) {
+                        float2 a = fmul2(lo2(xv[r][0]), lo2(xv[r][0]));
+                        a = ffma2(hi2(xv[r][0]), hi2(xv[r][0]), a);
+#pragma unroll
+                        for (int ch = 1; ch < PK_CH; ++ch) a = dot4(xv[r][ch], xv[r][ch], a);
+                        d[KT] = a.x + a.y;
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < SP1; ++q) v[rr * SP1 + q] = make_float2(d[2 * q], d[2 * q + 1]);
+            }
+            const float2 t = tr_reduce<S1>(v, tr, lane);
+            if (lane % TrCfg<S1>::LPS == 0 && lane / TrCfg<S1>::LPS < S1) cross1[(warp * NSUB + h) * 32 + lane / TrCfg<S1>::LPS] = t;
+        }
+        __syncthreads();
+        // every thread holds the batch in registers: refill the stage
+        if (tid == 0 && irow < r1) {
+            int br, bn2, bc2;
+            take(irow, ic, iend, br, bn2, bc2);
+            issue(s, br, bn2);
+        }
+        // lane r < R finishes row r: first-max argmax over the K dots, 1/||f||
+        const int my_r = lane < R ? lane : 0;
+        const int my_h = my_r / RS, my_base = (my_r % RS) * SP1;
+        float dk[2 * SP1];
+#pragma unroll
+        for (int j = 0; j < 2 * SP1; ++j) dk[j] = 0.f;
+#pragma unroll
+        for (int h = 0; h < NSUB; ++h) {
+            float2 tot = make_float2(0.f, 0.f);
+            if (lane < S1) {
+                tot = cross1[(0 * NSUB + h) * 32 + lane];
+#pragma unroll
+                for (int w = 1; w < PK_WARPS; ++w) tot = fadd2(tot, cross1[(w * NSUB + h) * 32 + lane]);   // fixed order
+            }
+#pragma unroll
+            for (int q = 0; q < SP1; ++q) {
+                const float tx = __shfl_sync(0xffffffffu, tot.x, my_base + q), ty = __shfl_sync(0xffffffffu, tot.y, my_base + q);
+                if (NSUB == 1 || my_h == h) { dk[2 * q] = tx; dk[2 * q + 1] = ty; }
+            }
+        }
+        int ks = 0;
+        if (has_l) {
+            float best = dk[0];
+#pragma unroll
+            for (int k = 1; k < KT; ++k)
+                if ((FULL || k < K) && dk[k] > best) { best = dk[k]; ks = k; }   // strict > : first max wins, like torch.argmax
+        }
+        // generate_data.py:747  f / f.norm(dim=-1, keepdim=True): applied as a per-row scale s = 1/||f||
+        const float s_l = normalize_f ? rsqrtf(dk[KT]) : 1.f;
+        int kr[R];
+        float ns[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) { kr[r] = __shfl_sync(0xffffffffu, ks, r); ns[r] = -__shfl_sync(0xffffffffu, s_l, r); }
+
+        // ---- pass 2 (fn = s f): ||g-fn||^2, ||l*-fn||^2, <f, g-fn>, <f, l*-fn> ----
+        float2 w2[S2];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            float2 aG = make_float2(0.f, 0.f), aL = aG, bG = aG, bL = aG;
+            if (r < bn && valid) {
+                const float2 m = make_float2(ns[r], ns[r]);
+                with_proto<KT, 0, KT>(l8, kr[r], [&](const float4 (&p)[PK_CH]) {
+#pragma unroll
+                    for (int ch = 0; ch < PK_CH; ++ch) {
+                        const float2 x0 = lo2(xv[r][ch]), x1 = hi2(xv[r][ch]);
+                        const float2 dg0 = ffma2(x0, m, lo2(g8[ch])), dg1 = ffma2(x1, m, hi2(g8[ch]));
+                        const float2 dl0 = ffma2(x0, m, lo2(p[ch])), dl1 = ffma2(x1, m, hi2(p[ch]));
+                        if (ch == 0) {
+                            aG = fmul2(dg0, dg0); aL = fmul2(dl0, dl0); bG = fmul2(x0, dg0); bL = fmul2(x0, dl0);
+                        } else {
+                            aG = ffma2(dg0, dg0, aG); aL = ffma2(dl0, dl0, aL); bG = ffma2(x0, dg0, bG); bL = ffma2(x0, dl0, bL);
+                        }
+                        aG = ffma2(dg1, dg1, aG); aL = ffma2(dl1, dl1, aL); bG = ffma2(x1, dg1, bG); bL = ffma2(x1, dl1, bL);
+                    }
+                });
+            }
+            w2[2 * r] = make_float2(aG.x + aG.y, aL.x + aL.y);
+            w2[2 * r + 1] = make_float2(bG.x + bG.y, bL.x + bL.y);
+        }
+        {
+            const float2 t = tr_reduce<S2>(w2, tr, lane);
+            if (lane % TrCfg<S2>::LPS == 0 && lane / TrCfg<S2>::LPS < S2) cross2[warp * 32 + lane / TrCfg<S2>::LPS] = t;
+        }
+        __syncthreads();
+        float2 tot2 = make_float2(0.f, 0.f);
+        if (lane < S2) {
+            tot2 = cross2[lane];
+#pragma unroll
+            for (int w = 1; w < PK_WARPS; ++w) tot2 = fadd2(tot2, cross2[w * 32 + lane]);
+        }
+        const float d2g = __shfl_sync(0xffffffffu, tot2.x, 2 * my_r), d2l = __shfl_sync(0xffffffffu, tot2.y, 2 * my_r);
+        const float fg = __shfl_sync(0xffffffffu, tot2.x, 2 * my_r + 1), fl = __shfl_sync(0xffffffffu, tot2.y, 2 * my_r + 1);
+        const float dg = has_g ? sqrtf(d2g) : 0.f, dl = has_l ? sqrtf(d2l) : 0.f;
+        // d||v||/dv = v/||v||, 0 at v = 0 (torch.norm's sub-gradient)
+        const float cg = (has_g && dg > 0.f) ? gs * invB / dg : 0.f;
+        const float cl = (has_l && dl > 0.f) ? ls * invB / dl : 0.f;
+        // d score/d fn = cg (fn-g) + cl (fn-l*);  chained through fn = f/||f||:  (that - fn <fn, that>) / ||f||
+        // <fn, fn-g> = -s <f, g-fn>.  Everything is linear in (f, g, l*):  grad = A f + Bg g + Bl l*
+        const float sd = normalize_f ? -s_l * (cg * fg + cl * fl) : 0.f;
+        const float A_l = (cg + cl - sd) * s_l * s_l, Bg_l = -cg * s_l, Bl_l = -cl * s_l;
+        if (warp == 0 && lane < bn) {
+            const float bad = __int_as_float(0x7fc00000);
+            per_sample[2 * orig_l] = valid ? dg : bad;   // out-of-range target poisons the score (NaN), loudly
+            per_sample[2 * orig_l + 1] = valid ? dl : bad;
+            kstar_out[orig_l] = valid ? ks : 0;
+        }
+        // ---- pass 3: gradient rows, written at the samples' original positions ----
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const float A = __shfl_sync(0xffffffffu, A_l, r), Bg = __shfl_sync(0xffffffffu, Bg_l, r);
+            const float Bl = __shfl_sync(0xffffffffu, Bl_l, r);
+            const int orig = __shfl_sync(0xffffffffu, orig_l, r);
+            if (r < bn) {
+                float4* orow = reinterpret_cast<float4*>(grad_f + (size_t)(unsigned)orig * (unsigned)D);
+                if (valid) {
+                    const float2 a2 = make_float2(A, A), bg2 = make_float2(Bg, Bg), bl2 = make_float2(Bl, Bl);
+                    with_proto<KT, 0, KT>(l8, kr[r], [&](const float4 (&p)[PK_CH]) {
+#pragma unroll
+                        for (int ch = 0; ch < PK_CH; ++ch) {
+                            float2 o0 = fmul2(lo2(xv[r][ch]), a2), o1 = fmul2(hi2(xv[r][ch]), a2);
+                            o0 = ffma2(lo2(g8[ch]), bg2, o0); o1 = ffma2(hi2(g8[ch]), bg2, o1);
+                            o0 = ffma2(lo2(p[ch]), bl2, o0); o1 = ffma2(hi2(p[ch]), bl2, o1);
+                            if (own[ch]) orow[chunk[ch]] = make_float4(o0.x, o0.y, o1.x, o1.y);
+                        }
+                    });
+                } else {
+                    const float bad = __int_as_float(0x7fc00000);
+#pragma unroll
+                    for (int ch = 0; ch < PK_CH; ++ch)
+                        if (own[ch]) orow[chunk[ch]] = make_float4(bad, bad, bad, bad);
+                }
+            }
+        }
+        if (++s == stages) { s = 0; parity ^= 1; }
+    }
+
+    // ---- deterministic batch mean by the last CTA (sample index order) ----
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) is_last = atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1;  // wraps back to 0
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        float sg = 0.f, sl = 0.f;
+        for (int i = tid; i < B; i += EN_THREADS) {
+            sg += __ldcg(per_sample + 2 * i);
+            sl += __ldcg(per_sample + 2 * i + 1);
+        }
+        fin[tid] = gs * sg + ls * sl;
+        __syncthreads();
+        for (int h = EN_THREADS / 2; h > 0; h >>= 1) {
+            if (tid < h) fin[tid] += fin[tid + h];
+            __syncthreads();
+        }
+        if (tid == 0) score[0] = fin[0] / (float)B;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+struct EnergyWs {
+    size_t ticket_off, ticket2_off, counts_off, off_off, rank_off, perm_off, total;
+};
+static EnergyWs energy_ws(int B, int C) {
+    auto up = [](size_t v) { return (v + 15) / 16 * 16; };
+    EnergyWs w;
+    w.ticket_off = 0;
+    w.ticket2_off = 4;
+    w.counts_off = 16;
+    w.off_off = up(w.counts_off + ((size_t)C + 1) * 4);
+    w.rank_off = up(w.off_off + ((size_t)C + 2) * 4);
+    w.perm_off = up(w.rank_off + (size_t)B * 4);
+    w.total = up(w.perm_off + (size_t)B * 4);
+    return w;
+}
+
+template <int CH>
 static int launch_energy(const float* f, const int64_t* target, const float* g, const float* l, int B, int D, int C, int K,
                          float gs, float ls, int normalize_f, float* score, float* per_sample, int32_t* kstar,
                          float* grad_f, unsigned int* ticket, cudaStream_t st) {
-    constexpr int SPB = EN_THREADS / GROUP;
-    const unsigned grid = (unsigned)((B + SPB - 1) / SPB);
+    const unsigned grid = (unsigned)B;
     if (K <= 4)
-        energy_kernel<GROUP, CH, 4><<<grid, EN_THREADS, 0, st>>>(f, target, g, l, B, D, C, K, gs, ls, normalize_f, score,
-                                                                per_sample, kstar, grad_f, ticket);
+        energy_kernel<EN_THREADS, CH, 4><<<grid, EN_THREADS, 0, st>>>(f, target, g, l, B, D, C, K, gs, ls, normalize_f, score,
+                                                                     per_sample, kstar, grad_f, ticket);
     else if (K <= 10)
-        energy_kernel<GROUP, CH, 10><<<grid, EN_THREADS, 0, st>>>(f, target, g, l, B, D, C, K, gs, ls, normalize_f, score,
-                                                                 per_sample, kstar, grad_f, ticket);
+        energy_kernel<EN_THREADS, CH, 10><<<grid, EN_THREADS, 0, st>>>(f, target, g, l, B, D, C, K, gs, ls, normalize_f, score,
+                                                                      per_sample, kstar, grad_f, ticket);
     else
-        energy_kernel<GROUP, CH, EN_MAXK><<<grid, EN_THREADS, 0, st>>>(f, target, g, l, B, D, C, K, gs, ls, normalize_f,
-                                                                      score, per_sample, kstar, grad_f, ticket);
+        energy_kernel<EN_THREADS, CH, EN_MAXK><<<grid, EN_THREADS, 0, st>>>(f, target, g, l, B, D, C, K, gs, ls, normalize_f,
+                                                                           score, per_sample, kstar, grad_f, ticket);
     DD_LAUNCH_OK();
     return 0;
 }
 
+template <int KT>
+static int launch_energy_tile(const float* f, const int64_t* target, const float* g, const float* l, int B, int D, int C, int K,
+                              float gs, float ls, int normalize_f, float* score, float* per_sample, int32_t* kstar,
+                              float* grad_f, unsigned char* ws, cudaStream_t st) {
+    const EnergyWs w = energy_ws(B, C);
+    unsigned int* ticket = (unsigned int*)(ws + w.ticket_off);
+    unsigned int* ticket2 = (unsigned int*)(ws + w.ticket2_off);
+    int* counts = (int*)(ws + w.counts_off);
+    int* off = (int*)(ws + w.off_off);
+    int* rank = (int*)(ws + w.rank_off);
+    int* perm = (int*)(ws + w.perm_off);
+    DD_CUDA_OK(cudaMemsetAsync(counts, 0, ((size_t)C + 1) * sizeof(int), st));
+    const unsigned pg = (unsigned)((B + EN_THREADS - 1) / EN_THREADS);
+    class_rank_kernel<<<pg, EN_THREADS, 0, st>>>(target, B, C, counts, rank, off, ticket2);
+    DD_LAUNCH_OK();
+    class_scatter_kernel<<<pg, EN_THREADS, 0, st>>>(target, B, C, rank, off, perm);
+    DD_LAUNCH_OK();
+    using Cfg = TileCfg<KT>;
+    const size_t ring_bytes = (Cfg::CTAS_PER_SM == 2 ? 100 * 1024 : 208 * 1024) - Cfg::SMEM_FIXED;
+    int stages = (int)(ring_bytes / ((size_t)ET_R * D * sizeof(float)));
+    if (stages > PK_MAX_STAGES) stages = PK_MAX_STAGES;
+    DD_REQUIRE(stages >= 2, DD_EUNSUPPORTED, "dd_energy_fwd_bwd: D=%d too large for the shared-memory ring", D);
+    const size_t smem = (size_t)stages * ET_R * D * sizeof(float) + Cfg::SMEM_FIXED;
+    const bool full = D == PK_MAX_D && K == KT && g && l;
+    auto kern = full ? energy_tile_kernel<KT, true> : energy_tile_kernel<KT, false>;
+    DD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int G = Cfg::CTAS_PER_SM * sm_count();
+    if (G > (B + ET_R - 1) / ET_R) G = (B + ET_R - 1) / ET_R;
+    kern<<<G, EN_THREADS, smem, st>>>(f, perm, off, g, l, B, D, C, K, gs, ls, normalize_f, score, per_sample, kstar, grad_f,
+                                      ticket, stages);
+    DD_LAUNCH_OK();
+    return 0;
+}
+
+// smallest B the class-tiled kernel takes in auto mode: below it the three extra tiny launches of the class
+// bucketing cost more than the L2 traffic they save
+static int tile_min_b() { return 16 * sm_count(); }
+
 }  // namespace dd
+
+extern "C" size_t dd_energy_workspace_bytes(int B, int C) {
+    if (B < 1 || C < 1) return 16;
+    return dd::energy_ws(B, C).total;
+}
 
 extern "C" int dd_energy_fwd_bwd(const float* f, const int64_t* target, const float* g, const float* l, int B, int D, int C,
                                  int K, float gs, float ls, int normalize_f, float* score, float* per_sample,
-                                 int32_t* kstar, float* grad_f, unsigned int* ticket, dd_stream_t stream) {
-    DD_REQUIRE(f && target && score && per_sample && kstar && grad_f && ticket, DD_EINVAL, "dd_energy_fwd_bwd: null pointer");
+                                 int32_t* kstar, float* grad_f, void* ws, size_t ws_bytes, int mode, dd_stream_t stream) {
+    DD_REQUIRE(f && target && score && per_sample && kstar && grad_f && ws, DD_EINVAL, "dd_energy_fwd_bwd: null pointer");
     DD_REQUIRE(B >= 1 && D >= 4 && C >= 1, DD_EINVAL, "dd_energy_fwd_bwd: bad sizes B=%d D=%d C=%d", B, D, C);
     DD_REQUIRE(D % 4 == 0, DD_EUNSUPPORTED, "dd_energy_fwd_bwd: D=%d must be a multiple of 4", D);
     DD_REQUIRE(!l || (K >= 1 && K <= dd::EN_MAXK), DD_EUNSUPPORTED, "dd_energy_fwd_bwd: K=%d outside 1..%d", K, dd::EN_MAXK);
     DD_REQUIRE(D <= 8192, DD_EUNSUPPORTED, "dd_energy_fwd_bwd: D=%d > 8192", D);
-    DD_REQUIRE(dd::aligned16(f) && dd::aligned16(g) && dd::aligned16(l) && dd::aligned16(grad_f), DD_EINVAL,
+    DD_REQUIRE(dd::aligned16(f) && dd::aligned16(g) && dd::aligned16(l) && dd::aligned16(grad_f) && dd::aligned16(ws), DD_EINVAL,
                "dd_energy_fwd_bwd: pointers must be 16-byte aligned");
+    DD_REQUIRE(ws_bytes >= 16, DD_EWORKSPACE, "dd_energy_fwd_bwd: workspace %zu < 16 bytes", ws_bytes);
     cudaStream_t st = (cudaStream_t)stream;
     if (!l) K = 0;
-#define ARGS f, target, g, l, B, D, C, K, gs, ls, normalize_f, score, per_sample, kstar, grad_f, ticket, st
-    const bool warp_map = B >= 16 * dd::sm_count() && D <= 2048;  // a warp per sample only pays with >= 16 warps per SM in flight
-    if (warp_map) {
-        if (D <= 512) return dd::launch_energy<32, 4>(ARGS);
-        if (D <= 1280) return dd::launch_energy<32, 10>(ARGS);
-        return dd::launch_energy<32, 16>(ARGS);
+    unsigned int* ticket = (unsigned int*)ws;
+    // large B: bucket by class and run the tile kernel (needs the full workspace); otherwise one CTA per sample
+    DD_REQUIRE(mode >= 0 && mode <= 2, DD_EINVAL, "dd_energy_fwd_bwd: mode %d (0 auto, 1 per-sample, 2 class-tiled)", mode);
+    const bool tile_ok = D <= dd::PK_MAX_D && ws_bytes >= dd::energy_ws(B, C).total;
+    DD_REQUIRE(mode != 2 || tile_ok, DD_EUNSUPPORTED, "dd_energy_fwd_bwd: class-tiled kernel needs D <= %d and a %zu-byte workspace",
+               dd::PK_MAX_D, dd::energy_ws(B, C).total);
+    if (mode == 2 || (mode == 0 && tile_ok && B >= dd::tile_min_b())) {
+#define ARGS f, target, g, l, B, D, C, K, gs, ls, normalize_f, score, per_sample, kstar, grad_f, (unsigned char*)ws, st
+        if (K <= 3) return dd::launch_energy_tile<3>(ARGS);
+        if (K <= 5) return dd::launch_energy_tile<5>(ARGS);
+        if (K <= 8) return dd::launch_energy_tile<8>(ARGS);
+        if (K <= 10) return dd::launch_energy_tile<10>(ARGS);
+        return dd::launch_energy_tile<dd::EN_MAXK>(ARGS);
+#undef ARGS
     }
-    if (D <= 2048) return dd::launch_energy<256, 2>(ARGS);
-    return dd::launch_energy<256, 8>(ARGS);
+#define ARGS f, target, g, l, B, D, C, K, gs, ls, normalize_f, score, per_sample, kstar, grad_f, ticket, st
+    if (D <= 2048) return dd::launch_energy<2>(ARGS);
+    return dd::launch_energy<8>(ARGS);
 #undef ARGS
 }

@@ -1,0 +1,67 @@
+// Row-streaming helpers shared by the persistent kernels (dd_proto.cu: K1 / K3, dd_energy.cu: K4 tile kernel):
+// transposed warp reduction, packed dot product, and the walk over class-sorted row batches.
+#pragma once
+#include "dd_common.cuh"
+
+namespace dd {
+
+constexpr int PK_THREADS = 256;
+constexpr int PK_WARPS = PK_THREADS / 32;
+constexpr int PK_CH = 2;          // float4 chunks owned per thread -> D <= 2048
+constexpr int PK_MAX_D = PK_THREADS * PK_CH * 4;
+constexpr int PK_MAX_STAGES = 12;
+constexpr size_t PK_RING_BYTES = 192 * 1024;
+
+__host__ __device__ constexpr int pow2_ge(int v) { return v <= 1 ? 1 : v <= 2 ? 2 : v <= 4 ? 4 : v <= 8 ? 8 : v <= 16 ? 16 : 32; }
+__host__ __device__ constexpr int log2i(int v) { return v <= 1 ? 0 : 1 + log2i(v / 2); }
+
+// Transposed warp reduction: every lane holds P partial values; afterwards lane L holds, in v[0], the
+// warp-wide sum of value index (L >> (5 - log2 P)).  Costs ~P shuffles instead of 5*P.
+template <int P, int OFF>
+__device__ __forceinline__ void xreduce(float (&v)[32], int lane) {
+    if constexpr (P > 1) {
+        const bool up = (lane & OFF) != 0;
+#pragma unroll
+        for (int i = 0; i < P / 2; ++i) {
+            const float keep = up ? v[i + P / 2] : v[i];
+            const float send = up ? v[i] : v[i + P / 2];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
+        }
+        xreduce<P / 2, OFF / 2>(v, lane);
+    } else if constexpr (OFF >= 1) {
+        v[0] += __shfl_xor_sync(0xffffffffu, v[0], OFF);
+        xreduce<1, OFF / 2>(v, lane);
+    }
+}
+
+// two packed FMAs per float4; the two halves of the accumulator are added once, by the caller
+__device__ __forceinline__ float2 dot4(const float4& a, const float4& b, float2 acc) {
+    acc = ffma2(make_float2(a.x, a.y), make_float2(b.x, b.y), acc);
+    return ffma2(make_float2(a.z, a.w), make_float2(b.z, b.w), acc);
+}
+
+// largest c with off[c] <= row  (=> off[c+1] > row because off[C] = N > row)
+template <typename OffT>
+__device__ __forceinline__ int find_class(const OffT* __restrict__ off, int C, int64_t row) {
+    int lo = 0, hi = C;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if ((int64_t)__ldg(off + mid) <= row) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// next batch of <= R rows of a single class, starting at the cursor.  `end` caches class_off[c+1] so the
+// common path touches no memory; only a class boundary reloads it.
+template <typename OffT>
+__device__ __forceinline__ void take_batch(const OffT* __restrict__ off, int64_t r1, int R, int64_t& row, int& c,
+                                           int64_t& end, int64_t& b_row, int& b_n, int& b_c) {
+    while (end <= row) { ++c; end = (int64_t)__ldg(off + c + 1); }
+    int64_t n = end - row;
+    if (n > R) n = R;
+    if (n > r1 - row) n = r1 - row;
+    b_row = row; b_n = (int)n; b_c = c;
+    row += n;
+}
+
+}  // namespace dd

@@ -7,7 +7,7 @@ every timed launch by READING a 512 MB buffer (a write-flush would leave dirty l
 bandwidth from the timed kernel), CUDA events on the launching stream, median of ``iters``.
 
 Algorithmic bytes per launch:
-  K5 fwd/bwd 5*B*16384*s   K6 2*B*16384*s   K7 3*B*16384*s   K4 B*(K+3)*D*4   K1 2*N*D*4+N*8   K3 N*D*4+2*N*4   K8 (B*3*512*512 + B*3*224*224)*s   K9 B*3*512*512*(s+1)
+  K5 fwd/bwd 5*B*16384*s   K6 2*B*16384*s   K7 3*B*16384*s   K4 2*B*D*4+(K+1)*C*D*4 (compulsory HBM bytes)   K1 2*N*D*4+N*8   K3 N*D*4+2*N*4   K8 (B*3*512*512 + B*3*224*224)*s   K9 B*3*512*512*(s+1)
 """
 from __future__ import annotations
 
@@ -107,12 +107,16 @@ def run(want=lambda name: True, iters=10, ks=(3, 5, 10), latent_dtypes=(torch.fl
         for K in (3, 10):
             g = torch.nn.functional.normalize(torch.randn(C, D, device=dev), dim=-1)
             l = torch.nn.functional.normalize(torch.randn(C, K, D, device=dev), dim=-1)
-            for B in (1, 16, 1024, 65536):
+            for B in (1, 16, 1024, 4096, 65536):
                 f = torch.randn(B, D, device=dev)
                 y = torch.randint(0, C, (B,), device=dev)
+                # bytes = compulsory HBM traffic (f read + grad written + the tables once); SURVEY's B*(K+3)*D*4 counts
+                # the per-sample prototype reads, which are L2 hits (tables <= 8 MB) -- kept as survey_bytes only
+                nbytes = 2 * B * D * 4 + (K + 1) * C * D * 4
                 for nf in (False, True):
-                    t = timeit(lambda: ops.energy_fwd_bwd(f, y, g, l, 1.0, 1.0, nf), iters)
-                    report(f"K4_energy_K{K}_B{B}_norm{int(nf)}", B * (K + 3) * D * 4, t, hbm_compulsory_bytes=2 * B * D * 4 + (K + 1) * C * D * 4)
+                    for mode in (("auto",) if B < 1024 else ("sample", "tile")):
+                        t = timeit(lambda: ops.energy_fwd_bwd(f, y, g, l, 1.0, 1.0, nf, mode=mode), iters)
+                        report(f"K4_energy_K{K}_B{B}_norm{int(nf)}_{mode}", nbytes, t, survey_bytes=B * (K + 3) * D * 4)
     if want("K8"):
         for dt in latent_dtypes:
             es = torch.empty(0, dtype=dt).element_size()

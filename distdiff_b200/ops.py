@@ -276,16 +276,18 @@ def add_noise(x: torch.Tensor, noise: torch.Tensor, a_t: float) -> torch.Tensor:
 # ------------------------------------------------------------------------------------------------
 # K4  prototype energy
 # ------------------------------------------------------------------------------------------------
-_tickets = {}
+_energy_ws = {}
 
 
-def _ticket(device: torch.device) -> torch.Tensor:
+def _energy_workspace(device: torch.device, B: int, C_: int) -> torch.Tensor:
+    """Zero-initialised K4 workspace (ticket + class-bucketing scratch), one per (device, stream), grown on demand.
+    Old buffers stay referenced: a captured CUDA graph may still hold their address."""
     key = (device.index, _stream())
-    t = _tickets.get(key)
-    if t is None:
-        t = torch.zeros(1, dtype=torch.int32, device=device)
-        _tickets[key] = t
-    return t
+    need = int(_lib.lib().dd_energy_workspace_bytes(B, C_))
+    held = _energy_ws.setdefault(key, [])
+    if not held or held[-1].numel() < need:
+        held.append(torch.zeros(max(need, 4096), dtype=torch.uint8, device=device))
+    return held[-1]
 
 
 def targets_tensor(targets, C_: int, device) -> torch.Tensor:
@@ -299,10 +301,14 @@ def targets_tensor(targets, C_: int, device) -> torch.Tensor:
     return torch.tensor(ts, dtype=torch.int64, device=device)
 
 
+ENERGY_MODES = {"auto": 0, "sample": 1, "tile": 2}
+
+
 def energy_fwd_bwd(f: torch.Tensor, targets, g: Optional[torch.Tensor], l: Optional[torch.Tensor], gs: float, ls: float,
-                   normalize_f: bool = False):
-    """One launch: (score[0-dim f32], per_sample [B,2], kstar [B] i32, d score/d f [B,D]).
-    generate_data.py:707-717 (normalize_f=False) / :747-759 (True)."""
+                   normalize_f: bool = False, mode: str = "auto"):
+    """(score[0-dim f32], per_sample [B,2], kstar [B] i32, d score/d f [B,D]) -- forward AND analytic gradient.
+    generate_data.py:707-717 (normalize_f=False) / :747-759 (True).  ``mode``: "auto" (by size), "sample" (one CTA per
+    sample, one launch) or "tile" (class-bucketed persistent kernel for large batches)."""
     f = _req(f, "image_features", torch.float32)
     if f.dim() != 2:
         raise DistDiffError("image_features must be [B, D]")
@@ -327,10 +333,14 @@ def energy_fwd_bwd(f: torch.Tensor, targets, g: Optional[torch.Tensor], l: Optio
     per = torch.empty(B, 2, dtype=torch.float32, device=f.device)
     kstar = torch.empty(B, dtype=torch.int32, device=f.device)
     grad = torch.empty_like(f)
-    _call("dd_energy_fwd_bwd", B * D * 4 * (2 + int(g is not None) + (K if l is not None else 0)), 1,
+    ws = _energy_workspace(f.device, B, Cn)
+    # algorithmic bytes (compulsory HBM traffic): f read + grad written + the prototype tables once
+    tiled = mode == "tile" or (mode == "auto" and D <= 2048 and
+                               B >= 16 * torch.cuda.get_device_properties(f.device).multi_processor_count)
+    _call("dd_energy_fwd_bwd", 2 * B * D * 4 + (int(g is not None) + (K if l is not None else 0)) * Cn * D * 4, 3 if tiled else 1,
           _ptr(f), _ptr(y), _ptr(g), _ptr(l), B, D, Cn, K, float(gs), float(ls),
                                        int(bool(normalize_f)), _ptr(score), _ptr(per), _ptr(kstar), _ptr(grad),
-                                       _ptr(_ticket(f.device)), _stream())
+                                       _ptr(ws), ws.numel(), ENERGY_MODES[mode], _stream())
     return score.reshape(()), per, kstar, grad
 
 

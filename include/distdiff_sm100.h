@@ -110,10 +110,16 @@ int dd_image_to_uint8(const void* img, int64_t B, int C, int H, int W, int dtype
  * f: [B,D] f32; target: [B] i64 in [0,C); g: [C,D] f32 or NULL; l: [C,K,D] f32 or NULL (prototypes are
  * used as given -- the caller normalises them once, generate_data.py:1113-1127).
  * Outputs: score [1] f32 (deterministic fixed-order sum), per_sample [B,2] f32 (the two distances),
- * kstar [B] i32, grad_f [B,D] f32.  ticket: [1] u32 device word, zero before first use (self-resetting). */
+ * kstar [B] i32, grad_f [B,D] f32.
+ * ws: caller-owned device workspace, 16-byte aligned, ZERO before first use (the kernels leave it reusable); one
+ * workspace per stream.  >= 16 bytes always works (one CTA per sample); with dd_energy_workspace_bytes(B, C)
+ * bytes a large batch (B >= 16 x #SMs, D <= 2048) is bucketed by class and runs the class-tiled kernel (prototype
+ * slices in registers, sample rows gathered by TMA) -- same results, HBM-bound instead of L2-bound.
+ * mode: 0 = choose by size, 1 = one CTA per sample, 2 = class-tiled (needs the full workspace). */
+size_t dd_energy_workspace_bytes(int B, int C);
 int dd_energy_fwd_bwd(const float* f, const int64_t* target, const float* g, const float* l, int B, int D, int C,
                       int K, float gs, float ls, int normalize_f, float* score, float* per_sample, int32_t* kstar,
-                      float* grad_f, unsigned int* ticket, dd_stream_t stream);
+                      float* grad_f, void* ws, size_t ws_bytes, int mode, dd_stream_t stream);
 
 /* ---- K1/K2: feature normalisation, class gather, class means --------------------------------------
  * Replaces dataloader.py:677 (f / ||f||), :678-697 (D2H + python per-class gather) and :707 (class mean).

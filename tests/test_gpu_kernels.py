@@ -203,13 +203,14 @@ def _energy_case(B, C, K, D, seed, dup=False):
                                      (5, 4, 1, 512), (1024, 100, 3, 2048), (2000, 50, 10, 2048), (1500, 7, 5, 512),
                                      (64, 1000, 3, 2048)])   # last: ImageNet-scale tables, BASELINE configs[4]
 @pytest.mark.parametrize("normalize_f", [False, True])
-def test_energy_vs_oracle(ops, cuda_device, B, C, K, D, normalize_f):
+@pytest.mark.parametrize("mode", ["sample", "tile"])   # one CTA per sample / class-bucketed tile kernel (large-B path)
+def test_energy_vs_oracle(ops, cuda_device, B, C, K, D, normalize_f, mode):
     f, gp, lp, y = _energy_case(B, C, K, D, 10 + B)
     for G, L in ((gp, lp), (gp, None), (None, lp)):
         s_ref, per_ref, k_ref, g_ref = energy.energy_fwd_bwd(f.numpy(), y, None if G is None else G.numpy(),
                                                              None if L is None else L.numpy(), 0.7, 1.3, normalize_f)
         score, per, kstar, grad = ops.energy_fwd_bwd(f.to(cuda_device), y, None if G is None else G.to(cuda_device),
-                                                     None if L is None else L.to(cuda_device), 0.7, 1.3, normalize_f)
+                                                     None if L is None else L.to(cuda_device), 0.7, 1.3, normalize_f, mode=mode)
         assert abs(float(score) - float(s_ref)) <= 1e-5 * abs(float(s_ref))
         assert np.allclose(per.cpu().numpy(), per_ref, rtol=1e-5, atol=1e-6)
         if L is not None:
@@ -248,6 +249,39 @@ def test_energy_ties_and_zero_distance(ops, cuda_device):
     f2 = gp[y2].clone()
     score, per, _, grad = ops.energy_fwd_bwd(f2.to(cuda_device), y2, gp.to(cuda_device), None, 1.0, 1.0, False)
     assert float(score) == 0.0 and torch.count_nonzero(grad) == 0 and torch.isfinite(grad).all()
+
+
+@pytest.mark.parametrize("K", [1, 3, 5, 8, 10, 16])
+def test_energy_tile_matches_sample_kernel(ops, cuda_device, K):
+    """auto mode at B >= 16 x SMs takes the class-tiled kernel; it must agree with the per-sample kernel on the same
+    inputs (ragged classes, an empty class, unsorted targets), for every register-tile instantiation."""
+    B, C, D = 5000, 37, 2048
+    f, gp, lp, y = _energy_case(B, C, K, D, 100 + K)
+    y = [v if v != 5 else 6 for v in y]          # class 5 stays empty
+    args = (f.to(cuda_device), y, gp.to(cuda_device), lp.to(cuda_device), 1.0, 0.5)
+    for nf in (False, True):
+        a = ops.energy_fwd_bwd(*args, nf, mode="sample")
+        b = ops.energy_fwd_bwd(*args, nf, mode="auto")
+        c = ops.energy_fwd_bwd(*args, nf, mode="tile")
+        assert torch.equal(b[0], c[0]) and torch.equal(b[3], c[3])        # auto == tile, bit for bit
+        assert abs(float(a[0]) - float(b[0])) <= 2e-6 * abs(float(a[0]))
+        assert torch.allclose(a[1], b[1], rtol=2e-6, atol=1e-7)
+        assert (a[2] != b[2]).float().mean() < 1e-3                         # only fp32-level argmax ties may differ
+        assert (a[3] - b[3]).norm() <= 2e-6 * a[3].norm()
+
+
+def test_energy_tile_bad_target_is_poisoned(ops, cuda_device):
+    B, C, K, D = 300, 6, 3, 512
+    f, gp, lp, y = _energy_case(B, C, K, D, 3)
+    yt = torch.tensor(y, dtype=torch.int64)
+    yt[7] = C
+    yt[200] = -1
+    for mode in ("sample", "tile"):
+        score, per, kstar, grad = ops.energy_fwd_bwd(f.to(cuda_device), yt.to(cuda_device), gp.to(cuda_device), lp.to(cuda_device),
+                                                     1.0, 1.0, False, mode=mode)
+        assert torch.isnan(score) and torch.isnan(grad[7]).all() and torch.isnan(grad[200]).all()
+        ok = torch.ones(B, dtype=torch.bool); ok[7] = ok[200] = False
+        assert torch.isfinite(grad.cpu()[ok]).all() and torch.isfinite(per.cpu()[ok]).all()
 
 
 def test_energy_deterministic_and_bad_target(ops, cuda_device):

@@ -283,7 +283,7 @@ class_scatter_kernel(const int64_t* __restrict__ target, int B, int C, const int
 // ---------------------------------------------------------------------------------------------------
 // large B: class-sorted tile kernel
 // ---------------------------------------------------------------------------------------------------
-constexpr int ET_R = 4;  // samples per batch (one ring stage)
+constexpr int ET_R = 4;   // samples per batch (one ring stage)
 
 // Warp sum of S packed (float2) partials per lane through a warp-private shared-memory transposition: every lane
 // stores its S partials (STS.64 into tr[slot][lane]); LPS = 32 / pow2(S) lanes then share a slot row, each adds its
@@ -327,15 +327,18 @@ __device__ __forceinline__ float2 tr_reduce(const float2 (&v)[S], float2* tr, in
 template <int KT>
 struct TileCfg {
     static constexpr int R = ET_R;
-    static constexpr int SP1 = (KT + 2) / 2;                 // packed slots per row in pass 1: K dots + |f|^2
+    static constexpr int NV = KT + 2;                        // reduced values per row in pass 1: K dots, <f,g>, |f|^2
+    static constexpr int SP1 = (NV + 1) / 2;                 // ... packed in pairs
     static constexpr int RS = (32 / SP1) >= R ? R : (32 / SP1);   // rows per reduction round
     static constexpr int NSUB = (R + RS - 1) / RS;
     static constexpr int S1 = RS * SP1;                      // slots per round
-    static constexpr int S2 = R * 2;                         // pass 2: (|fn-g|^2, |fn-l*|^2), (<f,g-fn>, <f,l*-fn>) per row
-    static constexpr int TR_FLOAT2S = TrCfg<S1>::FLOAT2S > TrCfg<S2>::FLOAT2S ? TrCfg<S1>::FLOAT2S : TrCfg<S2>::FLOAT2S;
-    static constexpr int CTAS_PER_SM = KT <= 5 ? 2 : 1;
+    static constexpr int S2 = R * 2;                         // exact pass: (|fn-g|^2, |fn-l*|^2), (<f,g-fn>, <f,l*-fn>) per row
+    static constexpr int SPN = (KT + 2) / 2;                 // prototype norms: |l_k|^2 (k < KT), |g|^2
+    static constexpr int TR_A = TrCfg<S1>::FLOAT2S > TrCfg<S2>::FLOAT2S ? TrCfg<S1>::FLOAT2S : TrCfg<S2>::FLOAT2S;
+    static constexpr int TR_FLOAT2S = TR_A > TrCfg<SPN>::FLOAT2S ? TR_A : TrCfg<SPN>::FLOAT2S;
+    static constexpr int CTAS_PER_SM = KT <= 4 ? 2 : 1;
     static constexpr size_t SMEM_FIXED = PK_MAX_STAGES * sizeof(uint64_t) + (size_t)PK_WARPS * TR_FLOAT2S * sizeof(float2) +
-                                         (size_t)PK_WARPS * (NSUB + 1) * 32 * sizeof(float2);
+                                         (size_t)PK_WARPS * (2 * NSUB + 1) * 32 * sizeof(float2);
 };
 
 // run body(p) with p = the K-th prototype slice, K CTA-uniform: a tree of uniform branches around COPIES of the body,
@@ -354,7 +357,19 @@ __device__ __forceinline__ void with_proto(const float4 (&l8)[KT][PK_CH], int k,
 
 __device__ __forceinline__ float2 lo2(const float4& v) { return make_float2(v.x, v.y); }
 __device__ __forceinline__ float2 hi2(const float4& v) { return make_float2(v.z, v.w); }
+__device__ __forceinline__ float2 dot4_first(const float4& a, const float4& b) {
+    return ffma2(hi2(a), hi2(b), fmul2(lo2(a), lo2(b)));
+}
 
+// One batch = <= R samples of one class.  Per batch and thread (8 owned columns):
+//   pass 1   K dots <f,l_k>, <f,g>, |f|^2 against the register-resident prototype slices -> warp transposition ->
+//            one shared-memory hop across the 8 warps (ONE __syncthreads per batch);
+//   finish   (lane r finishes row r, every warp redundantly) k* = first argmax, s = 1/||f||, and the two distances
+//            from the dots:  ||fn-p||^2 = |fn|^2 - 2 s <f,p> + |p|^2  (|p|^2 reduced once per class run);
+//   exact    only if some distance of the batch is so small that the expansion loses accuracy
+//            (d^2 < (|fn|^2+|p|^2)/8, e.g. f on its prototype): direct sums of (p - fn)^2 like the reference,
+//            one more reduction round + barrier.  CTA-uniform decision;
+//   pass 3   grad = A f + Bg g + Bl l*  (the chain rule through f/||f|| folded into the three coefficients).
 // FULL: D == 2048 (every thread owns both of its chunks), K == KT, both prototype tables present -> no predicates
 template <int KT, bool FULL>
 __global__ void __launch_bounds__(EN_THREADS, TileCfg<KT>::CTAS_PER_SM)
@@ -363,7 +378,7 @@ energy_tile_kernel(const float* __restrict__ f, const int* __restrict__ perm, co
                    int normalize_f, float* __restrict__ score, float* __restrict__ per_sample, int32_t* __restrict__ kstar_out,
                    float* __restrict__ grad_f, unsigned int* __restrict__ ticket, int stages) {
     using Cfg = TileCfg<KT>;
-    constexpr int R = Cfg::R, SP1 = Cfg::SP1, RS = Cfg::RS, NSUB = Cfg::NSUB, S1 = Cfg::S1, S2 = Cfg::S2;
+    constexpr int R = Cfg::R, NV = Cfg::NV, SP1 = Cfg::SP1, RS = Cfg::RS, NSUB = Cfg::NSUB, S1 = Cfg::S1, S2 = Cfg::S2, SPN = Cfg::SPN;
     static_assert(SP1 <= 32, "KT too large");
     const int D = FULL ? PK_MAX_D : D_;
     const int K = FULL ? KT : K_;
@@ -372,8 +387,10 @@ energy_tile_kernel(const float* __restrict__ f, const int* __restrict__ perm, co
     float* ring = reinterpret_cast<float*>(smem_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)stages * stage_elems * sizeof(float));
     float2* tr_all = reinterpret_cast<float2*>(full + PK_MAX_STAGES);          // [PK_WARPS][TR_FLOAT2S]
-    float2* cross1 = tr_all + PK_WARPS * Cfg::TR_FLOAT2S;                     // [PK_WARPS][NSUB][32]
-    float2* cross2 = cross1 + PK_WARPS * NSUB * 32;                           // [PK_WARPS][32]
+    // cross1 is double-buffered by batch parity: with one barrier per batch a fast warp writes the partials of batch
+    // i+1 while a slow one still reads those of batch i (it cannot get two batches ahead)
+    float2* cross1_all = tr_all + PK_WARPS * Cfg::TR_FLOAT2S;                 // [2][PK_WARPS][NSUB][32]
+    float2* cross2 = cross1_all + 2 * PK_WARPS * NSUB * 32;                   // [PK_WARPS][32]
     __shared__ float fin[EN_THREADS];
     __shared__ bool is_last;
 
@@ -405,34 +422,51 @@ energy_tile_kernel(const float* __restrict__ f, const int* __restrict__ perm, co
         b_row = row; b_n = n; b_c = c;
         row += n;
     };
-    auto issue = [&](int s, int br, int bn) {   // gather bn sample rows through the class-sort permutation
+    // gather bn sample rows through the class-sort permutation: lane i of warp 0 copies row i (src = perm[br + i])
+    auto issue = [&](int s, int bn, int src) {
         const uint32_t row_bytes = (uint32_t)D * sizeof(float);
-        mbar_expect_tx(&full[s], row_bytes * bn);
-        for (int i = 0; i < bn; ++i)
-            bulk_g2s(ring + s * stage_elems + i * D, f + (int64_t)__ldg(perm + br + i) * D, row_bytes, &full[s]);
+        if (lane == 0) mbar_expect_tx(&full[s], row_bytes * bn);
+        __syncwarp();
+        if (lane < bn) bulk_g2s(ring + s * stage_elems + lane * D, f + (int64_t)src * D, row_bytes, &full[s]);
     };
 
     int irow = r0, crow = r0;
     int ic = (r0 < r1) ? find_class(off, C + 1, r0) : 0;
     int cc = ic;
     int iend = (r0 < r1) ? __ldg(off + ic + 1) : 0, cend = iend;
-    if (tid == 0) {
+    if (warp == 0) {
         for (int s = 0; s < stages && irow < r1; ++s) {
             int br, bn, bc;
             take(irow, ic, iend, br, bn, bc);
-            issue(s, br, bn);
+            issue(s, bn, lane < bn ? __ldg(perm + br + lane) : 0);
         }
     }
-
     float4 g8[PK_CH], l8[KT][PK_CH];
+    float2 pn = make_float2(0.f, 0.f);   // lane q: (|p_2q|^2, |p_2q+1|^2), p = l_0 .. l_KT-1, g
     int cur = -1;
-    int s = 0;
+    int s = 0, flip = 0;
     uint32_t parity = 0;
-    while (crow < r1) {
-        int brow, bn, bc;
-        take(crow, cc, cend, brow, bn, bc);
+    // The permutation entries a batch needs (row sources of the refill, output rows of the batch) are loaded ONE
+    // ITERATION AHEAD: warp 0 would otherwise sit on an L2/DRAM round trip right before the CTA barrier.
+    int n_brow = 0, n_bn = 0, n_bc = 0, n_orig = 0;     // next batch to consume
+    int n_rf = 0, n_rf_src = 0;                          // next refill (warp 0)
+    if (crow < r1) {
+        take(crow, cc, cend, n_brow, n_bn, n_bc);
+        n_orig = lane < n_bn ? __ldg(perm + n_brow + lane) : 0;
+    }
+    if (warp == 0 && irow < r1) {
+        int br, bc2;
+        take(irow, ic, iend, br, n_rf, bc2);
+        n_rf_src = lane < n_rf ? __ldg(perm + br + lane) : 0;
+    }
+    while (n_bn > 0) {
+        const int brow = n_brow, bn = n_bn, bc = n_bc;
+        const int orig_l = n_orig;                        // lane r: original index of row r
+        const int rf_n = n_rf, rf_src = n_rf_src;
         const bool valid = bc < C;   // bucket C = out-of-range targets
-        if (bc != cur && valid) {
+        float2* cross1 = cross1_all + flip * (PK_WARPS * NSUB * 32);
+        flip ^= 1;
+        if (bc != cur && valid) {   // new class run: prototype slices into registers, their squared norms into `pn`
             cur = bc;
 #pragma unroll
             for (int ch = 0; ch < PK_CH; ++ch) {
@@ -442,8 +476,36 @@ energy_tile_kernel(const float* __restrict__ f, const int* __restrict__ perm, co
                     l8[k][ch] = (has_l && (FULL || k < K) && own[ch])
                                     ? __ldg(reinterpret_cast<const float4*>(l + ((int64_t)bc * K + k) * D) + chunk[ch]) : zero4;
             }
+            float nn[2 * SPN];
+#pragma unroll
+            for (int j = 0; j < 2 * SPN; ++j) nn[j] = 0.f;
+#pragma unroll
+            for (int k = 0; k < KT; ++k) {
+                float2 a = dot4_first(l8[k][0], l8[k][0]);
+#pragma unroll
+                for (int ch = 1; ch < PK_CH; ++ch) a = dot4(l8[k][ch], l8[k][ch], a);
+                nn[k] = a.x + a.y;
+            }
+            {
+                float2 a = dot4_first(g8[0], g8[0]);
+#pragma unroll
+                for (int ch = 1; ch < PK_CH; ++ch) a = dot4(g8[ch], g8[ch], a);
+                nn[KT] = a.x + a.y;
+            }
+            float2 vn[SPN];
+#pragma unroll
+            for (int q = 0; q < SPN; ++q) vn[q] = make_float2(nn[2 * q], nn[2 * q + 1]);
+            const float2 t = tr_reduce<SPN>(vn, tr, lane);
+            __syncthreads();   // cross2 may still be read by a slow warp of the previous batch's exact pass
+            if (lane % TrCfg<SPN>::LPS == 0 && lane / TrCfg<SPN>::LPS < SPN) cross2[warp * 32 + lane / TrCfg<SPN>::LPS] = t;
+            __syncthreads();
+            pn = make_float2(0.f, 0.f);
+            if (lane < SPN) {
+                pn = cross2[lane];
+#pragma unroll
+                for (int w = 1; w < PK_WARPS; ++w) pn = fadd2(pn, cross2[w * 32 + lane]);
+            }   // (the next write to cross2 is behind this batch's pass-1 barrier)
         }
-        const int orig_l = lane < bn ? __ldg(perm + brow + lane) : 0;   // lane r: original index of row r
         mbar_wait(&full[s], parity);
         const float* st = ring + s * stage_elems;
         float4 xv[R][PK_CH];
@@ -455,7 +517,7 @@ energy_tile_kernel(const float* __restrict__ f, const int* __restrict__ perm, co
                 else xv[r][ch] = own[ch] ? *reinterpret_cast<const float4*>(st + r * D + chunk[ch] * 4) : zero4;
             }
 
-        // ---- pass 1: K dots with the raw row + |f|^2, packed in pairs, RS rows per transposition round ----
+        // ---- pass 1: <f,l_k>, <f,g>, |f|^2 of the raw rows, packed in pairs, RS rows per transposition round ----
 #pragma unroll
         for (int h = 0; h < NSUB; ++h) {
             float2 v[S1];
@@ -469,19 +531,18 @@ energy_tile_kernel(const float* __restrict__ f, const int* __restrict__ perm, co
 #pragma unroll
                     for (int k = 0; k < KT; ++k) {
                         if (FULL || k < K) {
-                            float2 a = fmul2(lo2(xv[r][0]), lo2(l8[k][0]));
-                            a = ffma2(hi2(xv[r][0]), hi2(l8[k][0]), a);
+                            float2 a = dot4_first(xv[r][0], l8[k][0]);
 #pragma unroll
                             for (int ch = 1; ch < PK_CH; ++ch) a = dot4(xv[r][ch], l8[k][ch], a);
                             d[k] = a.x + a.y;
                         }
                     }
-                    if (normalize_f) {
-                        float2 a = fmul2(lo2(xv[r][0]), lo2(xv[r][0]));
-                        a = ffma2(hi2(xv[r][0]), hi2(xv[r][0]), a);
+                    {
+                        float2 a = dot4_first(xv[r][0], g8[0]), b = dot4_first(xv[r][0], xv[r][0]);
 #pragma unroll
-                        for (int ch = 1; ch < PK_CH; ++ch) a = dot4(xv[r][ch], xv[r][ch], a);
+                        for (int ch = 1; ch < PK_CH; ++ch) { a = dot4(xv[r][ch], g8[ch], a); b = dot4(xv[r][ch], xv[r][ch], b); }
                         d[KT] = a.x + a.y;
+                        d[KT + 1] = b.x + b.y;
                     }
                 }
 #pragma unroll
@@ -492,12 +553,9 @@ energy_tile_kernel(const float* __restrict__ f, const int* __restrict__ perm, co
         }
         __syncthreads();
         // every thread holds the batch in registers: refill the stage
-        if (tid == 0 && irow < r1) {
-            int br, bn2, bc2;
-            take(irow, ic, iend, br, bn2, bc2);
-            issue(s, br, bn2);
-        }
-        // lane r < R finishes row r: first-max argmax over the K dots, 1/||f||
+        if (warp == 0 && rf_n > 0) issue(s, rf_n, rf_src);
+
+        // ---- finish: lane r < R handles row r (every warp redundantly; no second barrier needed) ----
         const int my_r = lane < R ? lane : 0;
         const int my_h = my_r / RS, my_base = (my_r % RS) * SP1;
         float dk[2 * SP1];
@@ -518,64 +576,68 @@ energy_tile_kernel(const float* __restrict__ f, const int* __restrict__ perm, co
             }
         }
         int ks = 0;
+        float fl = dk[0];   // <f, l*>
         if (has_l) {
-            float best = dk[0];
 #pragma unroll
             for (int k = 1; k < KT; ++k)
-                if ((FULL || k < K) && dk[k] > best) { best = dk[k]; ks = k; }   // strict > : first max wins, like torch.argmax
+                if ((FULL || k < K) && dk[k] > fl) { fl = dk[k]; ks = k; }   // strict > : first max wins, like torch.argmax
         }
+        const float fg = dk[KT], ff = dk[KT + 1];
         // generate_data.py:747  f / f.norm(dim=-1, keepdim=True): applied as a per-row scale s = 1/||f||
-        const float s_l = normalize_f ? rsqrtf(dk[KT]) : 1.f;
+        const float s_l = normalize_f ? rsqrtf(ff) : 1.f;
+        const float fn2 = s_l * s_l * ff;                                      // |fn|^2
+        const float nlx = __shfl_sync(0xffffffffu, pn.x, ks >> 1), nly = __shfl_sync(0xffffffffu, pn.y, ks >> 1);
+        const float nl = (ks & 1) ? nly : nlx;                                 // |l*|^2
+        const float ng = __shfl_sync(0xffffffffu, (KT & 1) ? pn.y : pn.x, KT >> 1);   // |g|^2
+        float d2g = fmaf(-2.f * s_l, fg, fn2 + ng), d2l = fmaf(-2.f * s_l, fl, fn2 + nl);
+        float sg = fmaf(-s_l, fg, fn2), sl = fmaf(-s_l, fl, fn2);              // <fn, fn-g>, <fn, fn-l*>
+        const bool row_on = lane < bn && valid;
+        const bool small = row_on && ((has_g && !(d2g >= 0.125f * (fn2 + ng))) || (has_l && !(d2l >= 0.125f * (fn2 + nl))));
         int kr[R];
-        float ns[R];
 #pragma unroll
-        for (int r = 0; r < R; ++r) { kr[r] = __shfl_sync(0xffffffffu, ks, r); ns[r] = -__shfl_sync(0xffffffffu, s_l, r); }
-
-        // ---- pass 2 (fn = s f): ||g-fn||^2, ||l*-fn||^2, <f, g-fn>, <f, l*-fn> ----
-        float2 w2[S2];
+        for (int r = 0; r < R; ++r) kr[r] = __shfl_sync(0xffffffffu, ks, r);
+        if (__any_sync(0xffffffffu, small)) {
+            // ---- exact pass (fn = s f): ||g-fn||^2, ||l*-fn||^2, <f, g-fn>, <f, l*-fn> summed directly ----
+            float2 w2[S2];
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            float2 aG = make_float2(0.f, 0.f), aL = aG, bG = aG, bL = aG;
-            if (r < bn && valid) {
-                const float2 m = make_float2(ns[r], ns[r]);
-                with_proto<KT, 0, KT>(l8, kr[r], [&](const float4 (&p)[PK_CH]) {
+            for (int r = 0; r < R; ++r) {
+                float2 aG = make_float2(0.f, 0.f), aL = aG, bG = aG, bL = aG;
+                const float nsr = -__shfl_sync(0xffffffffu, s_l, r);
+                if (r < bn && valid) {
+                    const float2 m = make_float2(nsr, nsr);
+                    with_proto<KT, 0, KT>(l8, kr[r], [&](const float4 (&p)[PK_CH]) {
 #pragma unroll
-                    for (int ch = 0; ch < PK_CH; ++ch) {
-                        const float2 x0 = lo2(xv[r][ch]), x1 = hi2(xv[r][ch]);
-                        const float2 dg0 = ffma2(x0, m, lo2(g8[ch])), dg1 = ffma2(x1, m, hi2(g8[ch]));
-                        const float2 dl0 = ffma2(x0, m, lo2(p[ch])), dl1 = ffma2(x1, m, hi2(p[ch]));
-                        if (ch == 0) {
-                            aG = fmul2(dg0, dg0); aL = fmul2(dl0, dl0); bG = fmul2(x0, dg0); bL = fmul2(x0, dl0);
-                        } else {
+                        for (int ch = 0; ch < PK_CH; ++ch) {
+                            const float2 x0 = lo2(xv[r][ch]), x1 = hi2(xv[r][ch]);
+                            const float2 dg0 = ffma2(x0, m, lo2(g8[ch])), dg1 = ffma2(x1, m, hi2(g8[ch]));
+                            const float2 dl0 = ffma2(x0, m, lo2(p[ch])), dl1 = ffma2(x1, m, hi2(p[ch]));
                             aG = ffma2(dg0, dg0, aG); aL = ffma2(dl0, dl0, aL); bG = ffma2(x0, dg0, bG); bL = ffma2(x0, dl0, bL);
+                            aG = ffma2(dg1, dg1, aG); aL = ffma2(dl1, dl1, aL); bG = ffma2(x1, dg1, bG); bL = ffma2(x1, dl1, bL);
                         }
-                        aG = ffma2(dg1, dg1, aG); aL = ffma2(dl1, dl1, aL); bG = ffma2(x1, dg1, bG); bL = ffma2(x1, dl1, bL);
-                    }
-                });
+                    });
+                }
+                w2[2 * r] = make_float2(aG.x + aG.y, aL.x + aL.y);
+                w2[2 * r + 1] = make_float2(bG.x + bG.y, bL.x + bL.y);
             }
-            w2[2 * r] = make_float2(aG.x + aG.y, aL.x + aL.y);
-            w2[2 * r + 1] = make_float2(bG.x + bG.y, bL.x + bL.y);
-        }
-        {
             const float2 t = tr_reduce<S2>(w2, tr, lane);
             if (lane % TrCfg<S2>::LPS == 0 && lane / TrCfg<S2>::LPS < S2) cross2[warp * 32 + lane / TrCfg<S2>::LPS] = t;
-        }
-        __syncthreads();
-        float2 tot2 = make_float2(0.f, 0.f);
-        if (lane < S2) {
-            tot2 = cross2[lane];
+            __syncthreads();
+            float2 tot2 = make_float2(0.f, 0.f);
+            if (lane < S2) {
+                tot2 = cross2[lane];
 #pragma unroll
-            for (int w = 1; w < PK_WARPS; ++w) tot2 = fadd2(tot2, cross2[w * 32 + lane]);
+                for (int w = 1; w < PK_WARPS; ++w) tot2 = fadd2(tot2, cross2[w * 32 + lane]);
+            }
+            d2g = __shfl_sync(0xffffffffu, tot2.x, 2 * my_r); d2l = __shfl_sync(0xffffffffu, tot2.y, 2 * my_r);
+            sg = -s_l * __shfl_sync(0xffffffffu, tot2.x, 2 * my_r + 1); sl = -s_l * __shfl_sync(0xffffffffu, tot2.y, 2 * my_r + 1);
         }
-        const float d2g = __shfl_sync(0xffffffffu, tot2.x, 2 * my_r), d2l = __shfl_sync(0xffffffffu, tot2.y, 2 * my_r);
-        const float fg = __shfl_sync(0xffffffffu, tot2.x, 2 * my_r + 1), fl = __shfl_sync(0xffffffffu, tot2.y, 2 * my_r + 1);
-        const float dg = has_g ? sqrtf(d2g) : 0.f, dl = has_l ? sqrtf(d2l) : 0.f;
-        // d||v||/dv = v/||v||, 0 at v = 0 (torch.norm's sub-gradient)
-        const float cg = (has_g && dg > 0.f) ? gs * invB / dg : 0.f;
-        const float cl = (has_l && dl > 0.f) ? ls * invB / dl : 0.f;
-        // d score/d fn = cg (fn-g) + cl (fn-l*);  chained through fn = f/||f||:  (that - fn <fn, that>) / ||f||
-        // <fn, fn-g> = -s <f, g-fn>.  Everything is linear in (f, g, l*):  grad = A f + Bg g + Bl l*
-        const float sd = normalize_f ? -s_l * (cg * fg + cl * fl) : 0.f;
+        // 1/d through rsqrt (<= 2 ulp): d = d2 * rsqrt(d2);  d||v||/dv = v/||v||, 0 at v = 0 (torch.norm's sub-gradient)
+        const float ig = (has_g && d2g > 0.f) ? rsqrtf(d2g) : 0.f, il = (has_l && d2l > 0.f) ? rsqrtf(d2l) : 0.f;
+        const float dg = d2g * ig, dl = d2l * il;
+        const float cg = gs * invB * ig, cl = ls * invB * il;
+        // d score/d fn = cg (fn-g) + cl (fn-l*);  chained through fn = f/||f||:  (that - fn <fn, that>) / ||f||.
+        // Everything is linear in (f, g, l*):  grad = A f + Bg g + Bl l*
+        const float sd = normalize_f ? cg * sg + cl * sl : 0.f;
         const float A_l = (cg + cl - sd) * s_l * s_l, Bg_l = -cg * s_l, Bl_l = -cl * s_l;
         if (warp == 0 && lane < bn) {
             const float bad = __int_as_float(0x7fc00000);
@@ -611,6 +673,18 @@ energy_tile_kernel(const float* __restrict__ f, const int* __restrict__ perm, co
             }
         }
         if (++s == stages) { s = 0; parity ^= 1; }
+        // next iteration's permutation entries, issued after the last use of this iteration's (the scoreboard is
+        // in-order: a load issued earlier would make every later use of the OLD values wait for it as well)
+        n_bn = 0; n_rf = 0;
+        if (crow < r1) {
+            take(crow, cc, cend, n_brow, n_bn, n_bc);
+            n_orig = lane < n_bn ? __ldg(perm + n_brow + lane) : 0;
+        }
+        if (warp == 0 && irow < r1) {
+            int br, bc2;
+            take(irow, ic, iend, br, n_rf, bc2);
+            n_rf_src = lane < n_rf ? __ldg(perm + br + lane) : 0;
+        }
     }
 
     // ---- deterministic batch mean by the last CTA (sample index order) ----
@@ -739,7 +813,8 @@ extern "C" int dd_energy_fwd_bwd(const float* f, const int64_t* target, const fl
     if (mode == 2 || (mode == 0 && tile_ok && B >= dd::tile_min_b())) {
 #define ARGS f, target, g, l, B, D, C, K, gs, ls, normalize_f, score, per_sample, kstar, grad_f, (unsigned char*)ws, st
         if (K <= 3) return dd::launch_energy_tile<3>(ARGS);
-        if (K <= 5) return dd::launch_energy_tile<5>(ARGS);
+        if (K <= 4) return dd::launch_energy_tile<4>(ARGS);
+        if (K <= 6) return dd::launch_energy_tile<6>(ARGS);
         if (K <= 8) return dd::launch_energy_tile<8>(ARGS);
         if (K <= 10) return dd::launch_energy_tile<10>(ARGS);
         return dd::launch_energy_tile<dd::EN_MAXK>(ARGS);

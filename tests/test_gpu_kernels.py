@@ -270,6 +270,36 @@ def test_energy_tile_matches_sample_kernel(ops, cuda_device, K):
         assert (a[3] - b[3]).norm() <= 2e-6 * a[3].norm()
 
 
+@pytest.mark.parametrize("normalize_f", [False, True])
+def test_energy_tile_small_distances_take_the_exact_pass(ops, cuda_device, normalize_f):
+    """Samples on / next to their prototypes: the tile kernel's distance-from-dots expansion would lose accuracy there,
+    so the batch falls back to direct sums -- distances, score and gradient still match the oracle, exact zeros included."""
+    B, C, K, D = 257, 9, 4, 2048
+    f, gp, lp, y = _energy_case(B, C, K, D, 21)
+    f = torch.nn.functional.normalize(f, dim=-1) if not normalize_f else f
+    yt = torch.tensor(y)
+    scale = 3.7 if normalize_f else 1.0                       # direct mode normalises f first
+    f[0] = gp[yt[0]] * scale                                   # exactly on the class prototype
+    f[1] = lp[yt[1], 2] * scale                                # exactly on a group prototype
+    f[2:40] = (gp[yt[2:40]] + 1e-3 * torch.randn(38, D, generator=_g(5))) * scale
+    f[40:80] = (lp[yt[40:80], 1] + 3e-2 * torch.randn(40, D, generator=_g(6)) / D ** 0.5) * scale
+    s_ref, per_ref, k_ref, g_ref = energy.energy_fwd_bwd(f.numpy(), y, gp.numpy(), lp.numpy(), 1.0, 1.0, normalize_f)
+    score, per, kstar, grad = ops.energy_fwd_bwd(f.to(cuda_device), y, gp.to(cuda_device), lp.to(cuda_device), 1.0, 1.0,
+                                                 normalize_f, mode="tile")
+    assert abs(float(score) - float(s_ref)) <= 1e-5 * abs(float(s_ref))
+    assert np.allclose(per.cpu().numpy()[2:], per_ref[2:], rtol=2e-5, atol=1e-6)
+    assert np.allclose(per.cpu().numpy()[:2], per_ref[:2], rtol=1e-5, atol=2e-6)     # ~0 entries: fp32 rounding of fn
+    assert np.array_equal(kstar.cpu().numpy()[80:], k_ref[80:])
+    assert torch.isfinite(grad).all()
+    # the gradient of a ~zero distance is a unit vector of rounding noise in BOTH implementations: compare the rest
+    gn = np.linalg.norm(g_ref[80:])
+    assert np.linalg.norm(grad.cpu().numpy()[80:] - g_ref[80:]) <= 1e-5 * gn
+    if not normalize_f:
+        f2 = gp[yt[:8]].clone()
+        sc, pr, _, gr = ops.energy_fwd_bwd(f2.to(cuda_device), y[:8], gp.to(cuda_device), None, 1.0, 1.0, False, mode="tile")
+        assert float(sc) == 0.0 and torch.count_nonzero(gr) == 0
+
+
 def test_energy_tile_bad_target_is_poisoned(ops, cuda_device):
     B, C, K, D = 300, 6, 3, 512
     f, gp, lp, y = _energy_case(B, C, K, D, 3)

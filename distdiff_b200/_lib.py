@@ -53,6 +53,7 @@ SIGNATURES = {
     "dd_peer_header_bytes": (_z, []),
     "dd_peer_kmeans_exchange": (_i, [_p, _z, _z, _z, _z, _z, _i, _i, _p]),
     "dd_peer_status": (_i, [_p, _p, C.POINTER(_i)]),
+    "dd_peer_timing": (_i, [_p, _p, C.POINTER(C.c_double)]),
     "dd_kmeans_lloyd": (_i, [_p, _p, _l, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _z, _p, _p, _i, _p]),
     "dd_peer_destroy": (_i, [_p]),
 }

@@ -39,6 +39,16 @@ int sm_count();  // cached SM count of the current device (148 on B200)
         }                                                                                \
     } while (0)
 
+// internal entries of dd_proto.cu for the Lloyd loop in dd_peer.cu
+constexpr int KP_PDL = 2, KP_NO_REDUCE = 4;
+int kmeans_pass(const float* x_sorted, const int64_t* class_off, int64_t N, int D, int C, int K, const float* centroid,
+                const float* cnorm, int32_t* assign, double* sum, int64_t* cnt, double* inertia, void* ws, size_t ws_bytes,
+                int flags, cudaStream_t st);
+void kmeans_ws_slots(void* ws, int D, int C, int K, const double** ws_sum, const int64_t** ws_cnt, int* G);
+// centroid update; with `ws` it first adds the pass's partial slots (fixed order).  pdl: programmatic dependent launch
+int kmeans_update_launch(double* sum, int64_t* cnt, int C, int K, int D, float* centroid, float* cnorm, bool pdl, const void* ws,
+                         const int64_t* class_off, int64_t N, cudaStream_t st);
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // ---- 16-byte vector I/O with fp32 arithmetic --------------------------------------------------

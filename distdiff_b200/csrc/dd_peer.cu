@@ -18,6 +18,9 @@
 // NVLS all-reduce, needs two flag round trips instead of a collective launch, and replaces three launches by one.
 // Spins are bounded: a protocol failure sets the arena's status word (dd_peer_status) instead of hanging the GPU.
 #include "dd_common.cuh"
+#include "dd_stream.cuh"
+#include <stdlib.h>
+#include <string.h>
 #include "../../include/distdiff_sm100.h"
 
 namespace dd {
@@ -27,7 +30,9 @@ constexpr int PEER_THREADS = 256;
 constexpr int CPT = 8;              // columns per thread and pass of the exchange kernel
 constexpr size_t PEER_HDR = 1024;   // flag rows A [64], B [64], status, ticket (uint32)
 
-struct PeerBases { unsigned char* b[PEER_MAX]; };
+constexpr size_t PEER_STAMP_OFF = 544;   // 8 x u64 %globaltimer stamps of the last exchange (phase boundaries, dd_peer_timing)
+constexpr size_t PEER_TABLE_OFF = 640;   // peer arena base pointers [PEER_MAX] inside the header (device memory: a by-value
+                                         // kernel-parameter table indexed at run time would live in local memory)
 
 struct PeerCtx {
     int rank, world;
@@ -36,6 +41,7 @@ struct PeerCtx {
     unsigned char* peer[PEER_MAX];
     uint32_t epoch;
     int sm_count;
+    unsigned long long timeout_ns;
 };
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
@@ -46,43 +52,91 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-// wait until flags[0..world) all carry `epoch`; threads 0..world-1 poll one slot each.  Bounded (~2 s).
-__device__ __forceinline__ void wait_all(const uint32_t* flags, int world, uint32_t epoch, uint32_t* status) {
+// wait until flags[0..world) all carry `epoch`; threads 0..world-1 poll one slot each, bounded by timeout_ns of wall
+// time.  Returns false for the whole CTA on a timeout (status word = 1 + the slot that never arrived).
+__device__ __forceinline__ bool wait_all(const uint32_t* flags, int world, uint32_t epoch, uint32_t* status, unsigned long long timeout_ns) {
+    bool ok = true;
     if ((int)threadIdx.x < world) {
+        const unsigned long long t0 = global_ns();
         uint32_t spins = 0;
         while (ld_acquire_sys(flags + threadIdx.x) != epoch) {
-            __nanosleep(64);
-            if (++spins == (1u << 24)) { atomicExch(status, 1u + threadIdx.x); break; }
+            __nanosleep(32);
+            if ((++spins & 1023u) == 0 && global_ns() - t0 > timeout_ns) { atomicExch(status, 1u + threadIdx.x); ok = false; break; }
         }
     }
-    __syncthreads();
+    return __syncthreads_and(ok) != 0;
 }
 
 __global__ void __launch_bounds__(PEER_THREADS)
-kmeans_exchange_kernel(PeerBases P, int rank, int world, uint32_t epoch, size_t off_sum, size_t off_cnt, size_t off_cen,
-                       size_t off_cn, size_t off_gcnt, int R, int D) {
+kmeans_exchange_kernel(unsigned char* me, int rank, int world, uint32_t epoch, size_t off_sum, size_t off_cnt, size_t off_cen,
+                       size_t off_cn, size_t off_gcnt, int R, int D, unsigned long long timeout_ns,
+                       const double* __restrict__ ws_sum /* null: the local sums are final */, const int64_t* __restrict__ ws_cnt,
+                       const int64_t* __restrict__ class_off, int64_t N, int K, int G) {
     __shared__ double sh[PEER_THREADS / 32];
+    __shared__ unsigned char* peer[PEER_MAX];
     __shared__ bool last;
-    unsigned char* me = P.b[rank];
     uint32_t* flagA = reinterpret_cast<uint32_t*>(me);
     uint32_t* flagB = flagA + 64;
     uint32_t* status = flagA + 128;
     uint32_t* ticket = flagA + 129;
+    uint32_t* ticket0 = flagA + 130;
+    unsigned long long* stamp = reinterpret_cast<unsigned long long*>(me + PEER_STAMP_OFF);
+    if ((int)threadIdx.x < world) peer[threadIdx.x] = reinterpret_cast<unsigned char* const*>(me + PEER_TABLE_OFF)[threadIdx.x];
+    pdl_wait();                 // the local partial sums come from the K3 pass before this kernel
+    pdl_launch_dependents();    // the next K3 pass may run its prologue; it waits for this grid before touching centroids
+    __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x == 0) stamp[0] = global_ns();
 
-    // A: my partial sums are complete (previous kernel on this stream) -> tell everyone, wait for everyone
-    if (blockIdx.x == 0 && (int)threadIdx.x < world) {
+    // 0: the K3 pass left per-(CTA, class) partial slots: add them in the fixed order into this rank's local sums
+    //    (rows spread over the grid), so no separate reduce launch sits between the pass and the exchange
+    bool signal = blockIdx.x == 0;
+    if (ws_sum) {
+        double* my_sum = reinterpret_cast<double*>(me + off_sum);
+        int64_t* my_cnt = reinterpret_cast<int64_t*>(me + off_cnt);
+        for (int r = blockIdx.x; r < R; r += gridDim.x) {
+            double acc[SLOT_NC];
+            int64_t n;
+            slot_row_sum(ws_sum, ws_cnt, class_off, N, D, r / K, r % K, K, G, acc, n);
+#pragma unroll
+            for (int j = 0; j < SLOT_NC; ++j) {
+                const int col = threadIdx.x + j * PEER_THREADS;
+                if (col < D) my_sum[(size_t)r * D + col] = acc[j];
+            }
+            if (threadIdx.x == 0) my_cnt[r] = n;
+        }
         __threadfence_system();
-        st_release_sys(reinterpret_cast<uint32_t*>(P.b[threadIdx.x]) + rank, epoch);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned t = atomicAdd(ticket0, 1u);
+            last = (t == gridDim.x - 1);
+            if (last) *ticket0 = 0u;
+        }
+        __syncthreads();
+        signal = last;
+        if (last && threadIdx.x == 0) stamp[1] = global_ns();
     }
-    wait_all(flagA, world, epoch, status);
+    // A: my partial sums are complete -> tell everyone (one CTA), wait for everyone (all CTAs)
+    if (signal && (int)threadIdx.x < world) {
+        __threadfence_system();
+        st_release_sys(reinterpret_cast<uint32_t*>(peer[threadIdx.x]) + rank, epoch);
+    }
+    if (!wait_all(flagA, world, epoch, status, timeout_ns)) return;   // a rank is missing: reduce nothing, store nothing
+    if (blockIdx.x == 0 && threadIdx.x == 0) stamp[2] = global_ns();
 
     // 1 + 2: the centroid rows this rank owns
     const int lo = (int)((int64_t)R * rank / world), hi = (int)((int64_t)R * (rank + 1) / world);
     float* my_cen = reinterpret_cast<float*>(me + off_cen);
     for (int r = lo + blockIdx.x; r < hi; r += gridDim.x) {
         int64_t n = 0;
-        for (int p = 0; p < world; ++p) n += __ldcg(reinterpret_cast<const int64_t*>(P.b[p] + off_cnt) + r);
+        for (int p = 0; p < world; ++p) n += __ldcg(reinterpret_cast<const int64_t*>(peer[p] + off_cnt) + r);
         double sq = 0.0;
         // CPT columns per thread and pass; the loads of a pass (CPT per peer, peers unrolled by 4) are independent, so
         // one NVLink round trip serves the whole row instead of one per column
@@ -90,10 +144,10 @@ kmeans_exchange_kernel(PeerBases P, int rank, int world, uint32_t epoch, size_t 
             double s[CPT];
 #pragma unroll
             for (int j = 0; j < CPT; ++j) s[j] = 0.0;
-            if (n > 0) {
+            {   // (loaded even when the row turns out empty: the count loads above then overlap these instead of gating them)
 #pragma unroll 4
                 for (int p = 0; p < world; ++p) {
-                    const double* src = reinterpret_cast<const double*>(P.b[p] + off_sum) + (size_t)r * D;
+                    const double* src = reinterpret_cast<const double*>(peer[p] + off_sum) + (size_t)r * D;
                     double v[CPT];
 #pragma unroll
                     for (int j = 0; j < CPT; ++j) {
@@ -115,7 +169,7 @@ kmeans_exchange_kernel(PeerBases P, int rank, int world, uint32_t epoch, size_t 
                 }
             }
             for (int p = 0; p < world; ++p) {
-                float* dst = reinterpret_cast<float*>(P.b[p] + off_cen) + (size_t)r * D;
+                float* dst = reinterpret_cast<float*>(peer[p] + off_cen) + (size_t)r * D;
 #pragma unroll
                 for (int j = 0; j < CPT; ++j) {
                     const int col = c0 + threadIdx.x + j * PEER_THREADS;
@@ -126,8 +180,8 @@ kmeans_exchange_kernel(PeerBases P, int rank, int world, uint32_t epoch, size_t 
         const double t = block_sum_f64(sq, sh);
         if (threadIdx.x == 0) {
             for (int p = 0; p < world; ++p) {
-                reinterpret_cast<float*>(P.b[p] + off_cn)[r] = (float)t;
-                reinterpret_cast<int64_t*>(P.b[p] + off_gcnt)[r] = n;
+                reinterpret_cast<float*>(peer[p] + off_cn)[r] = (float)t;
+                reinterpret_cast<int64_t*>(peer[p] + off_gcnt)[r] = n;
             }
         }
         __syncthreads();
@@ -143,11 +197,31 @@ kmeans_exchange_kernel(PeerBases P, int rank, int world, uint32_t epoch, size_t 
     }
     __syncthreads();
     if (!last) return;
+    if (threadIdx.x == 0) stamp[3] = global_ns();
     if ((int)threadIdx.x < world) {
         __threadfence_system();
-        st_release_sys(reinterpret_cast<uint32_t*>(P.b[threadIdx.x]) + 64 + rank, epoch);
+        st_release_sys(reinterpret_cast<uint32_t*>(peer[threadIdx.x]) + 64 + rank, epoch);
     }
-    wait_all(flagB, world, epoch, status);
+    wait_all(flagB, world, epoch, status, timeout_ns);
+    if (threadIdx.x == 0) stamp[4] = global_ns();
+}
+
+static int exchange_launch(PeerCtx* c, size_t off_sum, size_t off_cnt, size_t off_cen, size_t off_cn, size_t off_gcnt, int R, int D,
+                           bool pdl, const double* ws_sum, const int64_t* ws_cnt, const int64_t* class_off, int64_t N, int K, int G,
+                           cudaStream_t st) {
+    const int rows = (int)((int64_t)R * (c->rank + 1) / c->world - (int64_t)R * c->rank / c->world);
+    int grid = ws_sum ? R : (rows < 1 ? 1 : rows);      // with the slot reduction every row of the table is local work
+    if (grid > 2 * c->sm_count) grid = 2 * c->sm_count;  // all CTAs spin on flags: they must be co-resident
+    c->epoch += 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(PEER_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    DD_CUDA_OK(cudaLaunchKernelEx(&cfg, kmeans_exchange_kernel, c->arena, c->rank, c->world, c->epoch, off_sum, off_cnt, off_cen, off_cn,
+                                  off_gcnt, R, D, c->timeout_ns, ws_sum, ws_cnt, class_off, N > 0 ? N : (int64_t)1, K, G));
+    return 0;
 }
 
 }  // namespace dd
@@ -160,6 +234,8 @@ int dd_peer_create(int rank, int world, size_t bytes, void** ctx, void* ipc_hand
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
     dd::PeerCtx* c = new dd::PeerCtx();
     c->rank = rank; c->world = world; c->bytes = bytes; c->epoch = 0;
+    c->timeout_ns = 10ull * 1000000000ull;   // DD_PEER_TIMEOUT_MS overrides: rank skew (a rank still compiling / loading) is not a failure
+    if (const char* e = getenv("DD_PEER_TIMEOUT_MS")) { const long long ms = atoll(e); if (ms > 0) c->timeout_ns = (unsigned long long)ms * 1000000ull; }
     for (int p = 0; p < dd::PEER_MAX; ++p) c->peer[p] = nullptr;
     void* mem = nullptr;
     cudaError_t e = cudaMalloc(&mem, bytes);
@@ -193,6 +269,7 @@ int dd_peer_connect(void* ctx, const void* all_handles) {
         DD_CUDA_OK(cudaIpcOpenMemHandle(&m, h, cudaIpcMemLazyEnablePeerAccess));
         c->peer[p] = (unsigned char*)m;
     }
+    DD_CUDA_OK(cudaMemcpy(c->arena + dd::PEER_TABLE_OFF, c->peer, sizeof(c->peer), cudaMemcpyHostToDevice));
     return 0;
 }
 
@@ -209,17 +286,9 @@ int dd_peer_kmeans_exchange(void* ctx, size_t off_sum, size_t off_cnt, size_t of
     for (int i = 0; i < 5; ++i) DD_REQUIRE(need[i] <= c->bytes, DD_EINVAL, "dd_peer_kmeans_exchange: buffer %d outside the arena", i);
     DD_REQUIRE(off_sum >= dd::PEER_HDR && off_sum % 16 == 0 && off_cnt % 8 == 0 && off_centroid % 16 == 0 && off_cnorm % 4 == 0 && off_gcnt % 8 == 0,
                DD_EINVAL, "dd_peer_kmeans_exchange: misaligned offsets");
-    dd::PeerBases P;
-    for (int p = 0; p < dd::PEER_MAX; ++p) P.b[p] = p < c->world ? c->peer[p] : nullptr;
-    for (int p = 0; p < c->world; ++p) DD_REQUIRE(P.b[p], DD_EINVAL, "dd_peer_kmeans_exchange: peer %d not connected", p);
-    const int rows = (int)((int64_t)R * (c->rank + 1) / c->world - (int64_t)R * c->rank / c->world);
-    int grid = rows < 1 ? 1 : rows;
-    if (grid > 2 * c->sm_count) grid = 2 * c->sm_count;
-    c->epoch += 1;
-    dd::kmeans_exchange_kernel<<<grid, dd::PEER_THREADS, 0, (cudaStream_t)stream>>>(P, c->rank, c->world, c->epoch, off_sum, off_cnt, off_centroid,
-                                                                                  off_cnorm, off_gcnt, R, D);
-    DD_LAUNCH_OK();
-    return 0;
+    for (int p = 0; p < c->world; ++p) DD_REQUIRE(c->peer[p], DD_EINVAL, "dd_peer_kmeans_exchange: peer %d not connected", p);
+    return dd::exchange_launch(c, off_sum, off_cnt, off_centroid, off_cnorm, off_gcnt, R, D, false, nullptr, nullptr, nullptr, 0, 1, 1,
+                               (cudaStream_t)stream);
 }
 
 // `iters` Lloyd iterations launched back to back from C: per iteration the K3 pass (+ its fixed-order partial reduce)
@@ -241,20 +310,42 @@ int dd_kmeans_lloyd(const float* x_sorted, const int64_t* class_off, int64_t N, 
             DD_REQUIRE(ptrs[i] && ptrs[i] >= lo && ptrs[i] < hi, DD_EINVAL, "dd_kmeans_lloyd: buffer %d is not inside the peer arena", i);
         o_sum = ptrs[0] - lo; o_cnt = ptrs[1] - lo; o_cen = ptrs[2] - lo; o_cn = ptrs[3] - lo; o_g = ptrs[4] - lo;
     }
+    // Per iteration TWO launches: the K3 pass, and the exchange -- the fused peer kernel or the centroid update, both of
+    // which add the pass's per-CTA partial slots themselves (fixed order) -- chained by programmatic dependent launch so
+    // the next pass's prologue (ring prefill from HBM) runs under the exchange's tail.  The NCCL path keeps the
+    // separate reduce launch (the all-reduce needs the local sums in place) and serves as the cross-check.
+    cudaStream_t st = (cudaStream_t)stream;
+    const double* ws_sum = nullptr;
+    const int64_t* ws_cnt = nullptr;
+    int G = 1;
+    const bool slots = !nccl_comm && N > 0 && D <= dd::PK_MAX_D;
+    if (slots) dd::kmeans_ws_slots(ws, D, C, K, &ws_sum, &ws_cnt, &G);
     for (int it = 0; it < iters; ++it) {
-        int rc = dd_kmeans_assign_accum(x_sorted, class_off, N, D, C, K, centroid, cnorm, assign, sum, cnt, nullptr, ws, ws_bytes, stream);
+        const int flags = (it == 0 ? 0 : dd::KP_PDL) | (slots ? dd::KP_NO_REDUCE : 0);
+        int rc = dd::kmeans_pass(x_sorted, class_off, N, D, C, K, centroid, cnorm, assign, sum, cnt, nullptr, ws, ws_bytes, flags, st);
         if (rc) return rc;
         if (peer_ctx) {
-            rc = dd_peer_kmeans_exchange(peer_ctx, o_sum, o_cnt, o_cen, o_cn, o_g, C * K, D, stream);
+            rc = dd::exchange_launch((dd::PeerCtx*)peer_ctx, o_sum, o_cnt, o_cen, o_cn, o_g, C * K, D, slots, ws_sum, ws_cnt, class_off, N, K, G, st);
         } else {
             if (nccl_comm) {
                 rc = dd_comm_allreduce(nccl_comm, sum, (size_t)C * K * D, cnt, (size_t)C * K, stream);
                 if (rc) return rc;
             }
-            rc = dd_kmeans_update(sum, cnt, C, K, D, centroid, cnorm, stream);
+            rc = dd::kmeans_update_launch(sum, cnt, C, K, D, centroid, cnorm, slots, slots ? ws : nullptr, class_off, N, st);
         }
         if (rc) return rc;
     }
+    return 0;
+}
+
+int dd_peer_timing(void* ctx, dd_stream_t stream, double* us5) {
+    DD_REQUIRE(ctx && us5, DD_EINVAL, "dd_peer_timing: null argument");
+    dd::PeerCtx* c = (dd::PeerCtx*)ctx;
+    unsigned long long t[5];
+    DD_CUDA_OK(cudaMemcpyAsync(t, c->arena + dd::PEER_STAMP_OFF, sizeof(t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    DD_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+    us5[0] = 0.0;
+    for (int i = 1; i < 5; ++i) us5[i] = t[i] >= t[0] ? (double)(t[i] - t[0]) * 1e-3 : -1.0;
     return 0;
 }
 

@@ -29,6 +29,16 @@ __device__ __forceinline__ void store_f64x4(double* dst, double a, double b, dou
     reinterpret_cast<double2*>(dst)[1] = make_double2(c, d);
 }
 
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// Programmatic dependent launch: everything before pdl_wait() (barrier init, class lookup, the first TMA loads of the
+// constant feature rows) overlaps the tail of the previous kernel on the stream; nothing that kernel wrote may be read
+// -- and nothing it still reads may be written -- before it.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------------------------------------------
 // K3: assign + accumulate
 // ---------------------------------------------------------------------------------------------------
@@ -100,6 +110,7 @@ kmeans_stream_kernel(const float* __restrict__ x, const int64_t* __restrict__ cl
         }
     };
 
+    pdl_wait();   // centroids / norms come from the previous kernel on the stream (the row loads above do not)
     int s = 0, buf = 0;
     uint32_t parity = 0;
     while (crow < r1) {
@@ -234,9 +245,6 @@ constexpr int K2_TR = 34;                      // float2 per transposition row: 
 constexpr int K2_MINK = 4;
 constexpr int K2_MAXK = 10;
 
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
 
 // acc[k] += row, k CTA-uniform: a binary tree of uniform branches (<= 4 levels) instead of a jump table
 // (the table costs a constant-bank load + indirect branch on the critical path of every row)
@@ -321,6 +329,7 @@ kmeans_pair_kernel(const float* __restrict__ x, const int64_t* __restrict__ clas
         int mu_class = -1;
         float2* my_tr = tr + (size_t)warp * SLOTS * K2_TR;
         const bool slot_ok = lane < SLOTS;
+        pdl_wait();   // centroids come from the previous kernel on the stream
         while (true) {
             mbar_wait(&full[stage], par);
             const int4 d = desc[stage];
@@ -449,6 +458,7 @@ kmeans_pair_kernel(const float* __restrict__ x, const int64_t* __restrict__ clas
             for (int k = 0; k < K; ++k) { ws_cnt[slot * K + k] = cnt_s[k]; cnt_s[k] = 0; }
         }
     };
+    pdl_wait();   // centroid norms (and the buffers written below) belong to the previous kernel until here
 
     while (true) {
         mbar_wait(&full[stage], par);  // descriptor + rows of this stage are visible
@@ -657,41 +667,15 @@ partial_reduce_kernel(const double* __restrict__ ws_sum, const int64_t* __restri
                       const double* __restrict__ ws_inertia, const int64_t* __restrict__ class_off, int64_t N, int D, int C,
                       int K, int G, double* __restrict__ sum, int64_t* __restrict__ cnt, double* __restrict__ inertia) {
     const int c = blockIdx.x / K, k = blockIdx.x % K;
-    const int64_t lo = class_off[c], hi = class_off[c + 1];
-    int g_lo = 0, g_hi = -1;
-    if (hi > lo) {  // CTA owning row r: g(r) = floor(((r+1)*G - 1) / N)
-        g_lo = (int)(((lo + 1) * G - 1) / N);
-        g_hi = (int)((hi * G - 1) / N);
-    }
-    // a CTA contributes iff its (possibly empty, when N < G) row range intersects the class
-    auto hits = [&](int g) {
-        const int64_t a = N * g / G, b = N * (g + 1) / G;
-        return (a > lo ? a : lo) < (b < hi ? b : hi);
-    };
-    // CTA loop outside, columns inside: the hit test (two 64-bit divisions) runs once per contributing CTA, and the
-    // PK_CH * 4 column loads of a slot are independent.  Same fixed g order as before -> bit-identical sums.
-    constexpr int NC = PK_MAX_D / PK_THREADS;
-    double acc[NC];
+    double acc[SLOT_NC];
+    int64_t n;
+    slot_row_sum(ws_sum, ws_cnt, class_off, N, D, c, k, K, G, acc, n);
 #pragma unroll
-    for (int j = 0; j < NC; ++j) acc[j] = 0.0;
-    for (int g = g_lo; g <= g_hi; ++g) {
-        if (!hits(g)) continue;
-        const double* src = ws_sum + (((int64_t)g + c) * K + k) * D;
-#pragma unroll
-        for (int j = 0; j < NC; ++j) {
-            const int col = threadIdx.x + j * PK_THREADS;
-            if (col < D) acc[j] += src[col];
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < NC; ++j) {
+    for (int j = 0; j < SLOT_NC; ++j) {
         const int col = threadIdx.x + j * PK_THREADS;
         if (col < D) sum[((int64_t)c * K + k) * D + col] = acc[j];
     }
     if (threadIdx.x == 0) {
-        int64_t n = 0;
-        for (int g = g_lo; g <= g_hi; ++g)
-            if (hits(g)) n += ws_cnt[((int64_t)g + c) * K + k];
         cnt[(int64_t)c * K + k] = n;
         if (blockIdx.x == 0 && inertia) {
             double t = 0.0;
@@ -743,22 +727,49 @@ kmeans_seed_kernel(const float* __restrict__ x, const int64_t* __restrict__ row_
     if (threadIdx.x == 0) cnt[r] = src >= 0 ? 1 : 0;
 }
 
+// centroid = fp32(sum / count) (an empty cluster keeps its centroid), ||centroid||^2.  With `ws_sum` the fixed-order
+// reduction of the K3 pass's per-CTA slots is done here as well (one launch per Lloyd iteration besides the pass): the
+// row's fp64 sum and count are formed from the slots, written to sum / cnt, and used.
 __global__ void __launch_bounds__(PK_THREADS)
-kmeans_update_kernel(const double* __restrict__ sum, const int64_t* __restrict__ cnt, int D, float* __restrict__ centroid,
-                     float* __restrict__ cnorm) {
+kmeans_update_kernel(double* __restrict__ sum, int64_t* __restrict__ cnt, int D, float* __restrict__ centroid,
+                     float* __restrict__ cnorm, const double* __restrict__ ws_sum, const int64_t* __restrict__ ws_cnt,
+                     const int64_t* __restrict__ class_off, int64_t N, int K, int G) {
     __shared__ double sh[PK_WARPS];
+    __shared__ int64_t s_n;
+    pdl_wait();                  // sums / counts / slots come from the K3 pass before this kernel
+    pdl_launch_dependents();     // the next pass may start its prologue (it waits for this grid before reading centroids)
     const int64_t r = blockIdx.x;
-    const int64_t n = cnt[r];
     double sq = 0.0;
-    for (int col = threadIdx.x; col < D; col += PK_THREADS) {
-        float m;
-        if (n > 0) {
-            m = (float)(sum[r * D + col] / (double)n);
-            centroid[r * D + col] = m;
-        } else {
-            m = centroid[r * D + col];  // an empty cluster keeps its centroid
+    if (ws_sum) {
+        double acc[SLOT_NC];
+        int64_t n;
+        slot_row_sum(ws_sum, ws_cnt, class_off, N, D, (int)(r / K), (int)(r % K), K, G, acc, n);
+        if (threadIdx.x == 0) { cnt[r] = n; s_n = n; }
+        __syncthreads();
+        n = s_n;
+#pragma unroll
+        for (int j = 0; j < SLOT_NC; ++j) {
+            const int col = threadIdx.x + j * PK_THREADS;
+            if (col < D) {
+                sum[r * D + col] = acc[j];
+                float m;
+                if (n > 0) { m = (float)(acc[j] / (double)n); centroid[r * D + col] = m; }
+                else m = centroid[r * D + col];
+                sq += (double)m * (double)m;
+            }
         }
-        sq += (double)m * (double)m;
+    } else {
+        const int64_t n = cnt[r];
+        for (int col = threadIdx.x; col < D; col += PK_THREADS) {
+            float m;
+            if (n > 0) {
+                m = (float)(sum[r * D + col] / (double)n);
+                centroid[r * D + col] = m;
+            } else {
+                m = centroid[r * D + col];  // an empty cluster keeps its centroid
+            }
+            sq += (double)m * (double)m;
+        }
     }
     const double t = block_sum_f64(sq, sh);
     if (threadIdx.x == 0) cnorm[r] = (float)t;
@@ -780,6 +791,19 @@ static WsLayout ws_layout(int D, int C, int K, int G) {
     return w;
 }
 
+// launch with the programmatic-stream-serialization attribute: the kernel may start (up to its pdl_wait()) while the
+// previous kernel on the stream drains
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 static int pick_stages(int R, int D, size_t ring_bytes = PK_RING_BYTES) {
     const size_t stage = (size_t)R * D * sizeof(float);
     int s = (int)(ring_bytes / stage);
@@ -793,14 +817,14 @@ static size_t smem_bytes(int stages, int R, int D) {
 template <int K, int R, bool INERTIA>
 static int launch_kmeans(const float* x, const int64_t* class_off, int64_t N, int D, int C, const float* centroid,
                          const float* cnorm, int32_t* assign, double* ws_sum, int64_t* ws_cnt, double* ws_inertia, int G,
-                         cudaStream_t st) {
+                         bool pdl, cudaStream_t st) {
     const int stages = pick_stages(R, D);
     DD_REQUIRE(stages >= 2, DD_EUNSUPPORTED, "kmeans: D=%d too large for the shared-memory ring", D);
     const size_t smem = smem_bytes(stages, R, D);
     auto kern = kmeans_stream_kernel<K, R, INERTIA>;
     DD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<G, PK_THREADS, smem, st>>>(x, class_off, N, D, C, centroid, cnorm, assign, ws_sum, ws_cnt, ws_inertia, stages);
-    DD_LAUNCH_OK();
+    DD_CUDA_OK(launch_pdl(kern, dim3(G), dim3(PK_THREADS), smem, st, pdl, x, class_off, N, D, C, centroid, cnorm, assign, ws_sum,
+                          ws_cnt, ws_inertia, stages));
     return 0;
 }
 
@@ -813,7 +837,8 @@ static size_t k2_smem_bytes(int stages, int D, int K) {
 
 template <int K>
 static int launch_kmeans_pair(const float* x, const int64_t* class_off, int64_t N, int D, int C, const float* centroid,
-                              const float* cnorm, int32_t* assign, double* ws_sum, int64_t* ws_cnt, int G, cudaStream_t st) {
+                              const float* cnorm, int32_t* assign, double* ws_sum, int64_t* ws_cnt, int G, bool pdl,
+                              cudaStream_t st) {
     const size_t limit = 227 * 1024;
     int stages = K2_CROSS;
     while (stages > 2 && k2_smem_bytes(stages, D, K) > limit) --stages;
@@ -821,8 +846,81 @@ static int launch_kmeans_pair(const float* x, const int64_t* class_off, int64_t 
     const size_t smem = k2_smem_bytes(stages, D, K);
     auto kern = (D == 8 * K2_COMPUTE) ? kmeans_pair_kernel<K, true> : kmeans_pair_kernel<K, false>;
     DD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<G, K2_THREADS, smem, st>>>(x, class_off, N, D, C, centroid, cnorm, assign, ws_sum, ws_cnt, stages);
-    DD_LAUNCH_OK();
+    DD_CUDA_OK(launch_pdl(kern, dim3(G), dim3(K2_THREADS), smem, st, pdl, x, class_off, N, D, C, centroid, cnorm, assign, ws_sum,
+                          ws_cnt, stages));
+    return 0;
+}
+
+// One K3 pass.  flags: KP_PDL = programmatic dependent launch behind the previous kernel on the stream; KP_NO_REDUCE =
+// leave the per-(CTA, class) partial slots in the workspace: the consumer (the slot-reducing centroid update, or the
+// peer exchange kernel) adds them in the same fixed order, saving the partial_reduce launch.
+int kmeans_pass(const float* x_sorted, const int64_t* class_off, int64_t N, int D, int C, int K, const float* centroid,
+                const float* cnorm, int32_t* assign, double* sum, int64_t* cnt, double* inertia, void* ws, size_t ws_bytes,
+                int flags, cudaStream_t st) {
+    DD_REQUIRE((x_sorted || N == 0) && class_off && centroid && cnorm && (assign || N == 0) && sum && cnt && ws, DD_EINVAL,
+               "dd_kmeans_assign_accum: null pointer");
+    DD_REQUIRE(N >= 0 && D >= 4 && C >= 1, DD_EINVAL, "dd_kmeans_assign_accum: bad sizes N=%lld D=%d C=%d", (long long)N, D, C);
+    DD_REQUIRE(K >= 1 && K <= 15, DD_EUNSUPPORTED, "dd_kmeans_assign_accum: K=%d outside 1..15", K);
+    DD_REQUIRE(D % 4 == 0 && D <= PK_MAX_D, DD_EUNSUPPORTED,
+               "dd_kmeans_assign_accum: D=%d must be a multiple of 4 and <= %d", D, PK_MAX_D);
+    DD_REQUIRE(aligned16(x_sorted) && aligned16(centroid) && aligned16(ws), DD_EINVAL,
+               "dd_kmeans_assign_accum: x_sorted / centroid / ws must be 16-byte aligned");
+    const int G = sm_count();
+    const WsLayout w = ws_layout(D, C, K, G);
+    DD_REQUIRE(ws_bytes >= w.total, DD_EWORKSPACE, "dd_kmeans_assign_accum: workspace %zu < %zu bytes", ws_bytes, w.total);
+    double* ws_sum = (double*)((char*)ws + w.sum_off);
+    int64_t* ws_cnt = (int64_t*)((char*)ws + w.cnt_off);
+    double* ws_in = (double*)((char*)ws + w.inertia_off);
+    const bool pdl = (flags & KP_PDL) != 0;
+    int rc = 0;
+    // K <= 3: the single-role streaming kernel is HBM-bound already (8 rows per reduction round, 81 % of peak);
+    // K = 4..10: the warp-specialised cluster-paired kernel; K > 10 or inertia requested: streaming kernel.
+    if (N > 0 && !inertia && K >= K2_MINK && K <= K2_MAXK) {
+#define DD_KP(KK) case KK: rc = launch_kmeans_pair<KK>(x_sorted, class_off, N, D, C, centroid, cnorm, assign, ws_sum, ws_cnt, G, pdl, st); break;
+        switch (K) { DD_KP(4) DD_KP(5) DD_KP(6) DD_KP(7) DD_KP(8) DD_KP(9) DD_KP(10) }
+#undef DD_KP
+        if (rc) return rc;
+    } else if (N > 0) {
+#define DD_KM(KK, RI, RF)                                                                                                   \
+    case KK:                                                                                                                \
+        rc = inertia ? launch_kmeans<KK, RI, true>(x_sorted, class_off, N, D, C, centroid, cnorm, assign, ws_sum, ws_cnt, ws_in, G, pdl, st) \
+                     : launch_kmeans<KK, RF, false>(x_sorted, class_off, N, D, C, centroid, cnorm, assign, ws_sum, ws_cnt, ws_in, G, pdl, st); \
+        break;
+        // rows per batch: with inertia R*(K+1) <= 32, without R*K <= 32 (capped by registers / ring stage size)
+        switch (K) {
+            DD_KM(1, 8, 8) DD_KM(2, 8, 8) DD_KM(3, 8, 8) DD_KM(4, 4, 8) DD_KM(5, 4, 6) DD_KM(6, 4, 5) DD_KM(7, 4, 4)
+            DD_KM(8, 2, 4) DD_KM(9, 2, 3) DD_KM(10, 2, 3) DD_KM(11, 2, 2) DD_KM(12, 2, 2)
+            DD_KM(13, 2, 2) DD_KM(14, 2, 2) DD_KM(15, 2, 2)
+        }
+#undef DD_KM
+        if (rc) return rc;
+    } else {
+        DD_CUDA_OK(cudaMemsetAsync(ws_in, 0, (size_t)G * sizeof(double), st));
+    }
+    if (!(flags & KP_NO_REDUCE)) {
+        partial_reduce_kernel<<<C * K, PK_THREADS, 0, st>>>(ws_sum, ws_cnt, ws_in, class_off, N > 0 ? N : 1, D, C, K, G, sum, cnt,
+                                                           inertia);
+        DD_LAUNCH_OK();
+    }
+    return 0;
+}
+
+// slot pointers of a pass's workspace, for the consumers that reduce the slots themselves
+void kmeans_ws_slots(void* ws, int D, int C, int K, const double** ws_sum, const int64_t** ws_cnt, int* G) {
+    *G = sm_count();
+    const WsLayout w = ws_layout(D, C, K, *G);
+    *ws_sum = (const double*)((char*)ws + w.sum_off);
+    *ws_cnt = (const int64_t*)((char*)ws + w.cnt_off);
+}
+
+int kmeans_update_launch(double* sum, int64_t* cnt, int C, int K, int D, float* centroid, float* cnorm, bool pdl,
+                         const void* ws /* null: sum / cnt are final */, const int64_t* class_off, int64_t N, cudaStream_t st) {
+    const double* ws_sum = nullptr;
+    const int64_t* ws_cnt = nullptr;
+    int G = 0;
+    if (ws) kmeans_ws_slots(const_cast<void*>(ws), D, C, K, &ws_sum, &ws_cnt, &G);
+    DD_CUDA_OK(launch_pdl(kmeans_update_kernel, dim3((unsigned)(C * K)), dim3(PK_THREADS), 0, st, pdl, sum, cnt, D, centroid, cnorm,
+                          ws_sum, ws_cnt, class_off, N > 0 ? N : (int64_t)1, K, G));
     return 0;
 }
 
@@ -896,58 +994,15 @@ int dd_kmeans_seed(const float* x_sorted, const int64_t* row_idx, int64_t R, int
 int dd_kmeans_update(const double* sum, const int64_t* cnt, int C, int K, int D, float* centroid, float* cnorm,
                      dd_stream_t stream) {
     DD_REQUIRE(sum && cnt && centroid && cnorm && C >= 1 && K >= 1 && D >= 1, DD_EINVAL, "dd_kmeans_update: bad arguments");
-    dd::kmeans_update_kernel<<<(unsigned)(C * K), dd::PK_THREADS, 0, (cudaStream_t)stream>>>(sum, cnt, D, centroid, cnorm);
-    DD_LAUNCH_OK();
-    return 0;
+    return dd::kmeans_update_launch(const_cast<double*>(sum), const_cast<int64_t*>(cnt), C, K, D, centroid, cnorm, false, nullptr, nullptr, 0,
+                                    (cudaStream_t)stream);
 }
 
 int dd_kmeans_assign_accum(const float* x_sorted, const int64_t* class_off, int64_t N, int D, int C, int K,
                            const float* centroid, const float* cnorm, int32_t* assign, double* sum, int64_t* cnt,
                            double* inertia, void* ws, size_t ws_bytes, dd_stream_t stream) {
-    DD_REQUIRE((x_sorted || N == 0) && class_off && centroid && cnorm && (assign || N == 0) && sum && cnt && ws, DD_EINVAL,
-               "dd_kmeans_assign_accum: null pointer");
-    DD_REQUIRE(N >= 0 && D >= 4 && C >= 1, DD_EINVAL, "dd_kmeans_assign_accum: bad sizes N=%lld D=%d C=%d", (long long)N, D, C);
-    DD_REQUIRE(K >= 1 && K <= 15, DD_EUNSUPPORTED, "dd_kmeans_assign_accum: K=%d outside 1..15", K);
-    DD_REQUIRE(D % 4 == 0 && D <= dd::PK_MAX_D, DD_EUNSUPPORTED,
-               "dd_kmeans_assign_accum: D=%d must be a multiple of 4 and <= %d", D, dd::PK_MAX_D);
-    DD_REQUIRE(dd::aligned16(x_sorted) && dd::aligned16(centroid) && dd::aligned16(ws), DD_EINVAL,
-               "dd_kmeans_assign_accum: x_sorted / centroid / ws must be 16-byte aligned");
-    const int G = dd::sm_count();
-    const dd::WsLayout w = dd::ws_layout(D, C, K, G);
-    DD_REQUIRE(ws_bytes >= w.total, DD_EWORKSPACE, "dd_kmeans_assign_accum: workspace %zu < %zu bytes", ws_bytes, w.total);
-    cudaStream_t st = (cudaStream_t)stream;
-    double* ws_sum = (double*)((char*)ws + w.sum_off);
-    int64_t* ws_cnt = (int64_t*)((char*)ws + w.cnt_off);
-    double* ws_in = (double*)((char*)ws + w.inertia_off);
-    int rc = 0;
-    // K <= 3: the single-role streaming kernel is HBM-bound already (8 rows per reduction round, 81 % of peak);
-    // K = 4..10: the warp-specialised cluster-paired kernel; K > 10 or inertia requested: streaming kernel.
-    if (N > 0 && !inertia && K >= dd::K2_MINK && K <= dd::K2_MAXK) {
-#define DD_KP(KK) case KK: rc = dd::launch_kmeans_pair<KK>(x_sorted, class_off, N, D, C, centroid, cnorm, assign, ws_sum, ws_cnt, G, st); break;
-        switch (K) { DD_KP(4) DD_KP(5) DD_KP(6) DD_KP(7) DD_KP(8) DD_KP(9) DD_KP(10) }
-#undef DD_KP
-        if (rc) return rc;
-    } else if (N > 0) {
-#define DD_KM(KK, RI, RF)                                                                                                   \
-    case KK:                                                                                                                \
-        rc = inertia ? dd::launch_kmeans<KK, RI, true>(x_sorted, class_off, N, D, C, centroid, cnorm, assign, ws_sum, ws_cnt, ws_in, G, st) \
-                     : dd::launch_kmeans<KK, RF, false>(x_sorted, class_off, N, D, C, centroid, cnorm, assign, ws_sum, ws_cnt, ws_in, G, st); \
-        break;
-        // rows per batch: with inertia R*(K+1) <= 32, without R*K <= 32 (capped by registers / ring stage size)
-        switch (K) {
-            DD_KM(1, 8, 8) DD_KM(2, 8, 8) DD_KM(3, 8, 8) DD_KM(4, 4, 8) DD_KM(5, 4, 6) DD_KM(6, 4, 5) DD_KM(7, 4, 4)
-            DD_KM(8, 2, 4) DD_KM(9, 2, 3) DD_KM(10, 2, 3) DD_KM(11, 2, 2) DD_KM(12, 2, 2)
-            DD_KM(13, 2, 2) DD_KM(14, 2, 2) DD_KM(15, 2, 2)
-        }
-#undef DD_KM
-        if (rc) return rc;
-    } else {
-        DD_CUDA_OK(cudaMemsetAsync(ws_in, 0, (size_t)G * sizeof(double), st));
-    }
-    dd::partial_reduce_kernel<<<C * K, dd::PK_THREADS, 0, st>>>(ws_sum, ws_cnt, ws_in, class_off, N > 0 ? N : 1, D, C, K, G, sum,
-                                                               cnt, inertia);
-    DD_LAUNCH_OK();
-    return 0;
+    return dd::kmeans_pass(x_sorted, class_off, N, D, C, K, centroid, cnorm, assign, sum, cnt, inertia, ws, ws_bytes, 0,
+                           (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -64,4 +64,42 @@ __device__ __forceinline__ void take_batch(const OffT* __restrict__ off, int64_t
     row += n;
 }
 
+// ---- fixed-order reduction of the per-(CTA, class) partial slots a streaming pass leaves in its workspace ----
+// CTA g of G owns rows [N g / G, N (g+1) / G) and stores its partial of class c in slot (g + c) (unique: CTA ranges
+// and classes are both ordered).  A 256-thread CTA adds the slots of row (c, k) in ascending g -- the one order used
+// everywhere (partial_reduce_kernel, the slot-reducing centroid update, the peer exchange), so all paths produce
+// bit-identical fp64 sums.
+constexpr int SLOT_NC = PK_MAX_D / PK_THREADS;   // columns per thread
+
+__device__ __forceinline__ bool cta_hits(int g, int G, int64_t N, int64_t lo, int64_t hi) {
+    const int64_t a = N * g / G, b = N * (g + 1) / G;
+    return (a > lo ? a : lo) < (b < hi ? b : hi);
+}
+
+__device__ __forceinline__ void slot_row_sum(const double* __restrict__ ws_sum, const int64_t* __restrict__ ws_cnt,
+                                             const int64_t* __restrict__ class_off, int64_t N, int D, int c, int k, int K, int G,
+                                             double (&acc)[SLOT_NC], int64_t& n) {
+    const int64_t lo = class_off[c], hi = class_off[c + 1];
+    int g_lo = 0, g_hi = -1;
+    if (hi > lo) {  // CTA owning row r: g(r) = floor(((r+1)*G - 1) / N)
+        g_lo = (int)(((lo + 1) * G - 1) / N);
+        g_hi = (int)((hi * G - 1) / N);
+    }
+    const bool dense = N >= G;   // every CTA owns rows: all of [g_lo, g_hi] contribute, no hit test needed
+#pragma unroll
+    for (int j = 0; j < SLOT_NC; ++j) acc[j] = 0.0;
+    n = 0;
+    // CTA loop outside, columns inside: the SLOT_NC column loads of a slot are independent
+    for (int g = g_lo; g <= g_hi; ++g) {
+        if (!dense && !cta_hits(g, G, N, lo, hi)) continue;
+        const double* src = ws_sum + (((int64_t)g + c) * K + k) * D;
+#pragma unroll
+        for (int j = 0; j < SLOT_NC; ++j) {
+            const int col = threadIdx.x + j * PK_THREADS;
+            if (col < D) acc[j] += __ldcg(src + col);
+        }
+        if (threadIdx.x == 0) n += __ldcg(ws_cnt + ((int64_t)g + c) * K + k);
+    }
+}
+
 }  // namespace dd

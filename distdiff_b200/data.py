@@ -52,21 +52,24 @@ class SyntheticCaltech(data.Dataset):
 
 class ImageFolderSorted(data.Dataset):
     def __init__(self, root, transform=None):
-        classes = sorted(d for d in os.listdir(root) if os.path.isdir(os.path.join(root, d)) and d not in CALTECH_DROP)
+        # dataloader.py:275-286: every entry of the train dir is a category (minus the two Caltech drops) and every entry
+        # of a category dir is a sample -- no extension filter; only the order differs (sorted, see the module docstring)
+        classes = [d for d in sorted(os.listdir(root)) if d not in CALTECH_DROP]
         self.class_names = [c.replace("_", " ") for c in classes]
         self.paths, self.targets = [], []
         for ci, c in enumerate(classes):
             for f in sorted(os.listdir(os.path.join(root, c))):
-                if f.lower().endswith((".jpg", ".jpeg", ".png", ".bmp")):
-                    self.paths.append(os.path.join(root, c, f))
-                    self.targets.append(ci)
+                self.paths.append(os.path.join(root, c, f))
+                self.targets.append(ci)
         self.transform = transform
 
     def __len__(self):
         return len(self.targets)
 
     def image(self, idx):
-        return Image.open(self.paths[idx]).convert("RGB")
+        from PIL.ImageOps import exif_transpose
+        image = exif_transpose(Image.open(self.paths[idx]))                    # dataloader.py:79-82
+        return image if image.mode == "RGB" else image.convert("RGB")
 
     def __getitem__(self, idx):
         img = self.image(idx)

@@ -107,7 +107,11 @@ class Expander:
         negative_prompt_embeds = batch["uncond_inputs_ids"].to(dev, dtype=wd, non_blocking=True)
         timesteps = self.timesteps
         model_input = batch["image_latents"].to(dev, dtype=wd, non_blocking=True)
-        noise = torch.randn_like(model_input)                                              # :1170 (CUDA default gen)
+        if getattr(a, "offset_noise", False):                                              # :1164-1168
+            noise = torch.randn_like(model_input) + 0.1 * torch.randn(model_input.shape[0], model_input.shape[1], 1, 1,
+                                                                       device=model_input.device, dtype=wd)
+        else:
+            noise = torch.randn_like(model_input)                                          # :1170 (CUDA default gen)
         start_index = guidance.start_index(a.strength, len(timesteps))                     # :1174
         t_enc = timesteps[start_index]
         noisy_model_input = self.sched.add_noise(model_input, noise, t_enc)                # :1176 (K7)

@@ -16,7 +16,7 @@ import os
 
 import torch
 
-from . import _lib, ops
+from . import _lib, eager_baseline as eager, ops
 
 _flush = None
 
@@ -92,17 +92,25 @@ def run(want=lambda name: True, iters=10, ks=(3, 5, 10), latent_dtypes=(torch.fl
                                                       gn.data_ptr() + n * es, gx.data_ptr(), torch.cuda.current_stream().cuda_stream), "bwd")
             report(f"K5_cfg_ddim_bwd_{dn}_B{B}", 5 * B * 16384 * es, timeit(bwd, iters))
             del gp, g0, gn, gx
-        B = 4096
-        x = torch.randn(B, 4, 64, 64, device=dev, dtype=dtype)
-        a = torch.rand(B, 4, 1, 1, device=dev)
-        b = torch.randn(B, 4, 1, 1, device=dev)
-        if want("K6"):
-            report(f"K6_affine_project_{dn}_B{B}", 2 * B * 16384 * es, timeit(lambda: ops.affine_project(x, a, b, 0.2), iters))
-        if want("K7"):
-            nz = torch.randn_like(x)
-            report(f"K7_add_noise_{dn}_B{B}", 3 * B * 16384 * es, timeit(lambda: ops.add_noise(x, nz, 0.3), iters))
-            del nz
-        del x
+        for B in (1, 8, 4096):
+            x = torch.randn(B, 4, 64, 64, device=dev, dtype=dtype)
+            a = torch.rand(B, 4, 1, 1, device=dev)
+            b = torch.randn(B, 4, 1, 1, device=dev)
+            if want("K6"):
+                report(f"K6_affine_project_{dn}_B{B}", 2 * B * 16384 * es, timeit(lambda: ops.affine_project(x, a, b, 0.2), iters))
+            if want("K7"):
+                nz = torch.randn_like(x)
+                report(f"K7_add_noise_{dn}_B{B}", 3 * B * 16384 * es, timeit(lambda: ops.add_noise(x, nz, 0.3), iters))
+                del nz
+            if want("eager"):   # the literal reference sequences on the same tensors (distdiff_b200/eager_baseline.py)
+                npred = torch.randn(2 * B, 4, 64, 64, device=dev, dtype=dtype)
+                nz = torch.randn_like(x)
+                with torch.no_grad():
+                    report(f"eager_K5_cfg_ddim_fwd_{dn}_B{B}", 5 * B * 16384 * es, timeit(lambda: eager.cfg_ddim_step(npred, x, 7.5, 0.3, 0.35), iters))
+                    report(f"eager_K6_affine_project_{dn}_B{B}", 2 * B * 16384 * es, timeit(lambda: eager.affine_project(x, a, b, 0.2), iters))
+                    report(f"eager_K7_add_noise_{dn}_B{B}", 3 * B * 16384 * es, timeit(lambda: eager.add_noise(x, nz, 0.3), iters))
+                del npred, nz
+            del x
     if want("K4"):
         for K in (3, 10):
             g = torch.nn.functional.normalize(torch.randn(C, D, device=dev), dim=-1)
@@ -117,6 +125,9 @@ def run(want=lambda name: True, iters=10, ks=(3, 5, 10), latent_dtypes=(torch.fl
                     for mode in (("auto",) if B < 1024 else ("sample", "tile")):
                         t = timeit(lambda: ops.energy_fwd_bwd(f, y, g, l, 1.0, 1.0, nf, mode=mode), iters)
                         report(f"K4_energy_K{K}_B{B}_norm{int(nf)}_{mode}", nbytes, t, survey_bytes=B * (K + 3) * D * 4)
+                    if want("eager") and K == 3:   # forward + autograd backward of generate_data.py:707-717 / :747-759
+                        yl = y.tolist() if B <= 16 else y
+                        report(f"eager_K4_energy_K{K}_B{B}_norm{int(nf)}", nbytes, timeit(lambda: eager.energy_fwd_bwd(f, yl, g, l, 1.0, 1.0, nf), iters))
     if want("K8"):
         for dt in latent_dtypes:
             es = torch.empty(0, dtype=dt).element_size()
@@ -154,6 +165,8 @@ def run(want=lambda name: True, iters=10, ks=(3, 5, 10), latent_dtypes=(torch.fl
         ws = ops.proto_workspace(D, C, 1, dev)
         if want("K1"):
             report(f"K1_rownorm_classsum_N{N}", 2 * N * D * 4 + N * 8, timeit(lambda: ops.rownorm_classsum(feat, perm, off, ws), iters))
+            if want("eager"):   # dataloader.py:677 + the per-class sums as index_add_ (the reference gathers on the CPU)
+                report(f"eager_K1_rownorm_classsum_N{N}", 2 * N * D * 4 + N * 8, timeit(lambda: eager.rownorm_classsum(feat, labels, C), iters))
         xs, _csum, _ccnt = ops.rownorm_classsum(feat, perm, off, ws)
         del feat
     if want("K3"):
@@ -163,6 +176,11 @@ def run(want=lambda name: True, iters=10, ks=(3, 5, 10), latent_dtypes=(torch.fl
             s, c = ops.kmeans_seed(xs, idx.contiguous())
             ops.kmeans_update(s, c, buf.centroid, buf.cnorm)
             report(f"K3_kmeans_assign_accum_N{N}_K{K}", N * D * 4 + 2 * N * 4, timeit(lambda: ops.kmeans_assign_accum(xs, off, buf), iters))
+            if want("eager") and K in (3, 10):   # one Lloyd iteration as centroid gather + cdist + argmin + index_add_
+                row_class = torch.repeat_interleave(torch.arange(C, device=dev), off[1:] - off[:-1])
+                report(f"eager_K3_kmeans_iteration_N{N}_K{K}", N * D * 4 + 2 * N * 4,
+                       timeit(lambda: eager.kmeans_iteration(xs, row_class, buf.centroid), max(3, iters // 2)))
+                del row_class
     if want("agglo"):
         for (Cc, n) in ((100, 30), (100, 100), (148, 300)):
             N2 = Cc * n

@@ -331,7 +331,9 @@ def create_model(model_name="resnet50", num_classes=100, pretrained=False, class
 
     model.forward_features = types.MethodType(forward_features, model)
     add_encoder_image_method(model)
-    if weight_path is not None and os.path.exists(weight_path):
+    if weight_path is not None:
+        if not os.path.exists(weight_path):   # the reference's torch.load would raise too (model_utils.py:89); never fall back to random init
+            raise FileNotFoundError(f"guide weights {weight_path!r} not found (--encoder_weight_path)")
         ck = torch.load(weight_path, map_location="cpu", weights_only=False)
         sd = ck.get("state_dict", ck)
         sd = {(k[len("module."):] if k.startswith("module.") else k): v for k, v in sd.items()}

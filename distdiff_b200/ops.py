@@ -479,7 +479,7 @@ def kmeans_assign_accum(x_sorted: torch.Tensor, class_off: torch.Tensor, buf: KM
     x_sorted = _req(x_sorted, "x_sorted", torch.float32)
     N, D = x_sorted.shape
     Cn, K, _ = buf.centroid.shape
-    _call("dd_kmeans_assign_accum", N * D * 4 + 2 * N * 4, 2,
+    _call("dd_kmeans_assign_accum", N * D * 4 + 2 * N * 4, 2 if want_inertia else 1,
           _ptr(x_sorted), _ptr(class_off), N, D, Cn, K, _ptr(buf.centroid), _ptr(buf.cnorm),
                                             _ptr(buf.assign), _ptr(buf.sum), _ptr(buf.cnt), _ptr(buf.inertia) if want_inertia else None, _ptr(buf.ws),
                                             buf.ws.numel(), _stream())
@@ -494,7 +494,7 @@ def kmeans_lloyd(x_sorted: torch.Tensor, class_off: torch.Tensor, buf: KMeansBuf
     Cn, K, _ = buf.centroid.shape
     peer = buf.arena.ctx if buf.arena is not None else None
     nccl = comm.handle if (comm is not None and peer is None) else None
-    _call("dd_kmeans_lloyd", int(iters) * (N * D * 4 + 2 * N * 4), 3 * int(iters),
+    _call("dd_kmeans_lloyd", int(iters) * (N * D * 4 + 2 * N * 4), 2 * int(iters),
           _ptr(x_sorted), _ptr(class_off), N, D, Cn, K, _ptr(buf.centroid), _ptr(buf.cnorm), _ptr(buf.assign), _ptr(buf.sum),
           _ptr(buf.cnt), _ptr(buf.gcnt), _ptr(buf.ws), buf.ws.numel(), nccl, peer, int(iters), _stream())
 
@@ -611,6 +611,12 @@ class PeerArena:
         v = C.c_int(0)
         check(_lib.lib().dd_peer_status(self.ctx, _stream(), C.byref(v)), "dd_peer_status")
         return int(v.value)
+
+    def timing(self):
+        """Phase boundaries (us since kernel start) of the last exchange on this rank: see dd_peer_timing."""
+        v = (C.c_double * 5)()
+        check(_lib.lib().dd_peer_timing(self.ctx, _stream(), v), "dd_peer_timing")
+        return [float(x) for x in v]
 
     def close(self) -> None:
         if self.ctx:

@@ -110,6 +110,24 @@ class NcclCollective(TorchDistCollective):
     def kmeans_lloyd(self, xs, off, buf, iters):
         ops.kmeans_lloyd(xs, off, buf, iters, comm=self.comm)
 
+    def close(self) -> None:
+        self.comm.close()
+
+
+def make_collective(prefer_peer: bool = True):
+    """The collective for the sharded prototype stage under torchrun: the fused peer-memory exchange when every GPU of
+    the job can map every other one (one node, NVLink / PCIe P2P -- CUDA IPC needs it), else plain NCCL.  All ranks
+    take the same decision (MIN over ranks)."""
+    import torch.distributed as dist
+    world = dist.get_world_size()
+    dev = torch.cuda.current_device()
+    ok = prefer_peer and world <= 16 and torch.cuda.device_count() >= world
+    if ok:
+        ok = all(torch.cuda.can_device_access_peer(dev, p) for p in range(torch.cuda.device_count()) if p != dev)
+    flag = torch.tensor([int(ok)], device=torch.device("cuda", dev))
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    return PeerCollective() if int(flag) == 1 else NcclCollective()
+
 
 class PeerCollective(NcclCollective):
     """NcclCollective whose per-iteration k-means exchange is the fused peer-memory kernel (csrc/dd_peer.cu): flag
@@ -294,21 +312,58 @@ def prototype_path(args) -> str:
     return os.path.join(save_dir, f"class_wise_prototype_K{args.K}.npz")
 
 
+def prototype_cache_key(args, model) -> str:
+    """What a cached prototype file depends on: guide architecture + a digest of its weights, the weight file identity,
+    the dataset location / synthetic shape, the cluster method and K.  Stored inside the .npz and compared on load, so a
+    different checkpoint, dataset or seed never reuses stale prototypes (the reference recomputes every run)."""
+    import hashlib
+    import json
+    h = hashlib.sha256()
+    with torch.no_grad():
+        for name, p in sorted(model.state_dict().items()):
+            t = p.detach().float().reshape(-1)
+            if t.numel():
+                # cheap, order-sensitive digest: a few moments + strided samples of every tensor (no full-model D2H)
+                idx = torch.linspace(0, t.numel() - 1, steps=min(64, t.numel()), device=t.device).long()
+                h.update(name.encode())
+                h.update(torch.cat([t[idx], t.sum()[None], t.abs().sum()[None]]).cpu().numpy().tobytes())
+    wp = getattr(args, "encoder_weight_path", None)
+    ident = None
+    if wp and os.path.exists(wp):
+        st = os.stat(wp)
+        ident = [os.path.abspath(wp), st.st_size, int(st.st_mtime)]
+    meta = {"arch": getattr(args, "arch", None), "weights_digest": h.hexdigest()[:32], "weight_file": ident,
+            "dataset": getattr(args, "dataset", None), "data_root": os.path.abspath(getattr(args, "data_root", "data")),
+            "synthetic": [getattr(args, "synthetic_classes", None), getattr(args, "synthetic_per_class", None)],
+            "seed": getattr(args, "seed", None), "tiny": bool(getattr(args, "tiny_models", False)),
+            "cluster_method": getattr(args, "cluster_method", "agglomerative"), "K": int(args.K)}
+    return json.dumps(meta, sort_keys=True)
+
+
 def extract_prototypes_with_encoder(args, model, trainset_factory: Optional[Callable] = None,
                                     coll: Optional[Collective] = None, cache: bool = True):
     """dataloader.py:734-747.  ``trainset_factory(args, transform)`` returns a dataset of (image, label);
-    default: distdiff_b200.data.load_trainset (Caltech-101-shaped folder or synthetic set)."""
+    default: distdiff_b200.data.load_trainset (Caltech-101-shaped folder or synthetic set).
+    ``cache``: reuse / write ``prototype_path(args)`` (the layout the reference left commented out); a cached file is used
+    only if its stored key (prototype_cache_key) matches this run."""
     from torch.utils import data as tdata
     from torchvision import transforms
     path = prototype_path(args)
     method = getattr(args, "cluster_method", "agglomerative")
-    have = cache and method == "agglomerative" and os.path.exists(path)
+    key = prototype_cache_key(args, model) if cache else None
+    have = False
+    if cache and method == "agglomerative" and os.path.exists(path):
+        try:
+            with np.load(path, allow_pickle=False) as z:
+                have = "cache_key" in z.files and str(z["cache_key"]) == key
+        except (OSError, ValueError):
+            have = False
     if coll is not None and coll.world > 1:          # one decision for all ranks: the stage below is collective
         box = [bool(have)]
         coll.dist.broadcast_object_list(box, src=0)
         have = box[0]
     if have:
-        z = np.load(path)
+        z = np.load(path, allow_pickle=False)
         return z["global_prototypes"], z["local_prototypes"]
     transform = transforms.Compose([                                            # dataloader.py:736-742
         transforms.Resize((224, 224)),
@@ -329,7 +384,7 @@ def extract_prototypes_with_encoder(args, model, trainset_factory: Optional[Call
     if cache and method == "agglomerative" and (coll is None or coll.rank == 0):
         os.makedirs(os.path.dirname(path), exist_ok=True)
         tmp = path + f".tmp{os.getpid()}.npz"
-        np.savez(tmp, global_prototypes=g, local_prototypes=l)
+        np.savez(tmp, global_prototypes=g, local_prototypes=l, cache_key=np.array(key))
         os.replace(tmp, path)                                                   # atomic: concurrent splits race-free
     return g, l
 

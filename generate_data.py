@@ -59,6 +59,7 @@ def parse_args(input_args=None):
     p.add_argument("--guidance_scale", type=float, default=7.5)                                              # :445
     p.add_argument("--do_classifier_free_guidance", type=bool, default=True)                                 # :453 (any non-empty string parses True upstream)
     p.add_argument("--offset_noise", action="store_true")                                                    # :558
+    p.add_argument("--text_to_img", action="store_true")                                                     # :1150 (pure-noise start; not built)
     p.add_argument("--mixed_precision", type=str, default=None)                                              # :523 (ignored upstream: fp16 hard-coded :1039)
     p.add_argument("--dataloader_num_workers", type=int, default=0)
     # ---- additions; defaults reproduce the reference ----
@@ -77,7 +78,30 @@ def parse_args(input_args=None):
     args, unknown = p.parse_known_args(input_args)
     if unknown:
         logging.getLogger("distdiff_b200").warning("ignoring flags that are not on the expansion path: %s", unknown)
+    # flags that change what is generated but are outside the hot path built here: refuse instead of silently ignoring
+    if args.text_to_img:
+        raise SystemExit("--text_to_img (generate_data.py:1150-1158, sampling from pure noise) is not implemented; the img2img path is")
+    if args.language_enhance:
+        raise SystemExit("--language_enhance (LLM-rewritten prompts, generate_data.py:239) is not implemented")
+    if args.optimize_targets is not None and args.encoder_weight_path is not None and not os.path.exists(args.encoder_weight_path):
+        raise SystemExit(f"--encoder_weight_path {args.encoder_weight_path!r} does not exist (the reference asserts this when "
+                         "--optimize_targets is set)")
     return args
+
+
+def build_guide(args, num_classes, device):
+    """The guide network is sized from the DATASET (len(class_names), like the reference), so a real checkpoint loads
+    strictly for any class count; missing weights raise (nets.create_model)."""
+    from distdiff_b200 import nets
+    if args.tiny_models:
+        guide = nets.create_model("resnet18", num_classes=num_classes)
+    else:
+        guide = nets.create_model(args.arch, num_classes=num_classes, weight_path=args.encoder_weight_path)
+        if args.encoder_weight_path is None and args.optimize_targets is not None:
+            logging.getLogger("distdiff_b200").warning("no --encoder_weight_path: the guide network is RANDOM-INIT (synthetic runs only)")
+    guide.requires_grad_(False)
+    guide.eval()
+    return guide.to(device)
 
 
 def build_models(args, device, weight_dtype):
@@ -85,11 +109,9 @@ def build_models(args, device, weight_dtype):
     if args.tiny_models:
         unet = nets.UNet2DConditionModel(block_out_channels=(32, 64, 64, 64), cross_attention_dim=768, heads=2)
         vae = nets.AutoencoderKL(chs=(32, 32, 64, 64))
-        guide = nets.create_model("resnet18", num_classes=args.synthetic_classes)
     else:
         unet = nets.UNet2DConditionModel()
         vae = nets.AutoencoderKL()
-        guide = nets.create_model(args.arch, num_classes=args.synthetic_classes, weight_path=args.encoder_weight_path)
     local = args.pretrained_model_name_or_path
     if local and os.path.isdir(local):
         for name, m in (("unet", unet), ("vae", vae)):
@@ -98,10 +120,10 @@ def build_models(args, device, weight_dtype):
                 m.load_state_dict(torch.load(f, map_location="cpu"))
     if args.gradient_checkpointing:
         unet.enable_gradient_checkpointing()                                                                # :1049-1050
-    for m in (unet, vae, guide):
+    for m in (unet, vae):
         m.requires_grad_(False)
         m.eval()
-    return unet.to(device), vae.to(device), guide.to(device)
+    return unet.to(device), vae.to(device)
 
 
 def main(args):
@@ -124,16 +146,19 @@ def main(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=device)
-        coll = prototypes.PeerCollective()
+        coll = prototypes.make_collective()   # fused peer exchange when every GPU maps every other one, else NCCL
         args.split, args.total_split = rank, world
         logging.getLogger("distdiff_b200").info("torchrun: rank %d of %d -> --split %d --total_split %d", rank, world, rank, world)
     if args.seed is not None:
         expand.set_seed(args.seed)                                                                          # :860-861
     weight_dtype = {"fp16": torch.float16, "bf16": torch.bfloat16, "fp32": torch.float32}[args.dtype]       # :1039
     noise_scheduler = DDIMScheduler.from_pretrained(args.pretrained_model_name_or_path, subfolder="scheduler")  # :863
-    unet, vae, image_encoder = build_models(args, device, weight_dtype)
+    unet, vae = build_models(args, device, weight_dtype)
 
-    # dataset + latents (VAE encode in fp32 like the reference, :983), then the --split block (:1001-1009)
+    # dataset + latents (VAE encode in fp32 like the reference, :983), then the --split block (:1001-1009).
+    # LIMITATION: there is no CLIP text encoder offline -- prompt embeddings come from a fixed random embedding table
+    # (deterministic per class name); images are NOT comparable with the reference's until a real text encoder is plugged
+    # in here.  Everything downstream of the embeddings is the reference's computation.
     embed = dd_data.random_text_embedder()
     only = None
     if args.shard_latents:      # opt-in: encode only this process's block (per-image generators; not the reference's draws)
@@ -145,6 +170,7 @@ def main(args):
 
     # prototypes (:1100-1127) -- guide in fp32 for extraction (dataloader.py:745), then cast (:1106)
     args.num_classes = len(dataset.class_names)
+    image_encoder = build_guide(args, args.num_classes, device)
     global_np, local_np = prototypes.extract_prototypes_with_encoder(args, image_encoder, coll=coll)
     if args.optimize_targets is not None:
         args.optimize_targets = args.optimize_targets.split("-")                                            # :1109

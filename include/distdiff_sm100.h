@@ -188,7 +188,8 @@ int dd_comm_destroy(void* comm);
  * carved out of the arena at the same offsets (>= dd_peer_header_bytes()) on every rank: sum [R,D] f64 and cnt [R]
  * i64 hold the LOCAL partial results on entry; centroid [R,D] f32, cnorm [R] f32 and gcnt [R] i64 (global counts)
  * are written for all R = C*K rows on every rank.  Every rank must make the same sequence of exchange calls.
- * dd_peer_status: non-zero if a bounded flag wait timed out (synchronises the stream). */
+ * dd_peer_status: non-zero if a bounded flag wait timed out (synchronises the stream); a timed-out exchange reduces
+ * nothing and stores nothing.  The bound is 10 s of wall time (DD_PEER_TIMEOUT_MS overrides it at dd_peer_create). */
 int dd_peer_create(int rank, int world, size_t bytes, void** ctx, void* ipc_handle_64);
 int dd_peer_connect(void* ctx, const void* all_handles);
 void* dd_peer_local(void* ctx);
@@ -196,6 +197,10 @@ size_t dd_peer_header_bytes(void);
 int dd_peer_kmeans_exchange(void* ctx, size_t off_sum, size_t off_cnt, size_t off_centroid, size_t off_cnorm, size_t off_gcnt,
                             int R, int D, dd_stream_t stream);
 int dd_peer_status(void* ctx, dd_stream_t stream, int* status);
+/* Phase boundaries of the LAST exchange on this rank, microseconds since its kernel started (device %globaltimer):
+ * us5 = {0, local slot reduce done, flag barrier A passed, owned rows reduced + stored, flag barrier B passed}.
+ * Diagnostic (synchronises the stream); -1 for a phase that did not run (e.g. no slot reduction). */
+int dd_peer_timing(void* ctx, dd_stream_t stream, double* us5);
 /* `iters` Lloyd iterations launched back to back from C (no host round trip between them): per iteration
  * dd_kmeans_assign_accum, then the exchange -- dd_peer_kmeans_exchange when peer_ctx is given (sum / cnt / centroid /
  * cnorm / gcnt must then lie inside the arena), else [dd_comm_allreduce when nccl_comm is given +] dd_kmeans_update.

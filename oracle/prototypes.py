@@ -10,7 +10,7 @@
   CUDA kernel implements): fp64 Euclidean matrix, repeated merge of the
   globally closest pair with the Lance-Williams average update, children
   stored (min id, max id) like scipy's ``label`` pass, then ``_hc_cut``'s heap
-  walk.  Pinned against sklearn in tests/test_oracle_prototypes.py.
+  walk.  Pinned against sklearn in tests/test_oracle_golden.py.
 * ``kmeans_*``: the north-star's per-class Lloyd k-means.  NOT reference
   behaviour (the reference is agglomerative, dataloader.py:699-705): parity is
   unpinned by the reference, this file is the specification:

@@ -17,7 +17,9 @@ def test_reference_arm_json_contract():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "expanded images/sec" and d["unit"] == "images/s"
     assert d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None and d["data"] == "synthetic"
-    assert d["value"] > 0 and abs(d["ms_per_step"] - 1e3 / d["value"]) < 1e-6 * d["ms_per_step"]
+    # a reference-arm step is one sampled DDIM step: value = (fraction of an image per step) / (measured time per step)
+    assert d["value"] > 0 and 0 < d["image_fraction_per_step"] < 1
+    assert abs(d["value"] - d["image_fraction_per_step"] / (d["ms_per_step"] * 1e-3)) < 1e-6 * d["value"]
     assert d["steps"] == 1 and d["warmup"] == 0 and d["n_gpus"] == 1 and d["gpu_launches"] == 0
     assert "workload" in d["config"] and "model" not in d["config"]
     cb = d["cpu_baseline"]

@@ -325,9 +325,9 @@ def run_ours(opt):
             peer.close()
         nccl.close()
 
-    def make_expander(graph):
+    def make_expander(graph, graph_guidance=True):
         return expand.Expander(a, unet, vae, guide, nets.VaeImageProcessor(), DDIMScheduler(), gproto, lproto, weight_dtype=wd, device=dev,
-                               use_cuda_graph=graph)
+                               use_cuda_graph=graph, graph_guidance=graph_guidance)
 
     size = 8 if opt.tiny else 64
     n_host = max(opt.steps, 1)
@@ -367,7 +367,8 @@ def run_ours(opt):
     swap = eager_baseline.swapped() if opt.ops == "eager" else None
     if swap is not None:
         swap.__enter__()
-    ex = make_expander(not opt.no_cuda_graph)
+    # (the eager sequences cannot be captured around the guided step: tensor_clamp's masked scatters synchronise)
+    ex = make_expander(not opt.no_cuda_graph, graph_guidance=opt.ops == "fused")
     expand.set_seed(a.seed)
     for i in range(max(opt.warmup, 1)):
         img, lat, info = ex.expand_batch(resident)
@@ -449,7 +450,7 @@ def run_ours(opt):
             if ctx is not None:
                 ctx.__enter__()
             try:
-                e = ex if (graph and not eager and not opt.no_cuda_graph) else make_expander(graph)
+                e = ex if (graph and not eager and not opt.no_cuda_graph) else make_expander(graph, graph_guidance=not eager)
                 expand.set_seed(a.seed)
                 e.expand_batch(resident); e.expand_batch(resident)
                 t, _, _ = timed(lambda i: e.expand_batch(resident), "dd_cmp_" + tag, n_cmp)

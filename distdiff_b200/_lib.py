@@ -39,7 +39,7 @@ SIGNATURES = {
     "dd_class_mean": (_i, [_p, _p, _l, _i, _p, _p, _p]),
     "dd_normalize_rows": (_i, [_p, _l, _i, _p, _p]),
     "dd_kmeans_seed": (_i, [_p, _p, _l, _i, _p, _p, _p]),
-    "dd_kmeans_assign_accum": (_i, [_p, _p, _l, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _z, _p]),
+    "dd_kmeans_assign_accum": (_i, [_p, _p, _l, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _z, _i, _p]),
     "dd_kmeans_update": (_i, [_p, _p, _i, _i, _i, _p, _p, _p]),
     "dd_agglo_workspace_bytes": (_z, [_l, _i]),
     "dd_agglo_average": (_i, [_p, _p, _i, _i, _i, _l, _p, _p, _p, _p, _p, _z, _p]),

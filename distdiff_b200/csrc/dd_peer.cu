@@ -57,8 +57,6 @@ __device__ __forceinline__ unsigned long long global_ns() {
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
 }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // wait until flags[0..world) all carry `epoch`; threads 0..world-1 poll one slot each, bounded by timeout_ns of wall
 // time.  Returns false for the whole CTA on a timeout (status word = 1 + the slot that never arrived).

@@ -24,21 +24,6 @@
 
 namespace dd {
 
-__device__ __forceinline__ void store_f64x4(double* dst, double a, double b, double c, double d) {
-    reinterpret_cast<double2*>(dst)[0] = make_double2(a, b);
-    reinterpret_cast<double2*>(dst)[1] = make_double2(c, d);
-}
-
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
-// Programmatic dependent launch: everything before pdl_wait() (barrier init, class lookup, the first TMA loads of the
-// constant feature rows) overlaps the tail of the previous kernel on the stream; nothing that kernel wrote may be read
-// -- and nothing it still reads may be written -- before it.
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-
 // ---------------------------------------------------------------------------------------------------
 // K3: assign + accumulate
 // ---------------------------------------------------------------------------------------------------
@@ -245,22 +230,6 @@ constexpr int K2_TR = 34;                      // float2 per transposition row: 
 constexpr int K2_MINK = 4;
 constexpr int K2_MAXK = 10;
 
-
-// acc[k] += row, k CTA-uniform: a binary tree of uniform branches (<= 4 levels) instead of a jump table
-// (the table costs a constant-bank load + indirect branch on the critical path of every row)
-template <int K, int LO, int HI>
-__device__ __forceinline__ void acc_add(f32x2_t (&acc)[K][4], int k, const float4& a, const float4& b) {
-    if constexpr (HI - LO == 1) {
-        acc[LO][0] = fadd2_s(acc[LO][0], a.x, a.y);
-        acc[LO][1] = fadd2_s(acc[LO][1], a.z, a.w);
-        acc[LO][2] = fadd2_s(acc[LO][2], b.x, b.y);
-        acc[LO][3] = fadd2_s(acc[LO][3], b.z, b.w);
-    } else {
-        constexpr int MID = (LO + HI) / 2;
-        if (k < MID) acc_add<K, LO, MID>(acc, k, a, b);
-        else acc_add<K, MID, HI>(acc, k, a, b);
-    }
-}
 
 // FULL: D == 8 * K2_COMPUTE (2048), every thread owns both of its chunks -> no predicates on the row loads.
 //
@@ -873,9 +842,16 @@ int kmeans_pass(const float* x_sorted, const int64_t* class_off, int64_t N, int 
     double* ws_in = (double*)((char*)ws + w.inertia_off);
     const bool pdl = (flags & KP_PDL) != 0;
     int rc = 0;
-    // K <= 3: the single-role streaming kernel is HBM-bound already (8 rows per reduction round, 81 % of peak);
-    // K = 4..10: the warp-specialised cluster-paired kernel; K > 10 or inertia requested: streaming kernel.
-    if (N > 0 && !inertia && K >= K2_MINK && K <= K2_MAXK) {
+    // K <= 3: the single-role streaming kernel is HBM-bound already (8 rows per reduction round, 85 % of peak);
+    // K = 4..10: the warp-specialised cluster-paired FMA kernel; K > 10 or inertia: streaming kernel.
+    // KP_MMA (opt-in): K = 4..10 with the distance products on the tensor cores (dd_kmeans_mma.cu, split-fp16 mma.sync,
+    // fp32-grade assignments).  Built and measured, NOT the default: 264 us vs 216 us per 100k x 2048 pass at K = 10
+    // (profiles/r2_k3_mma.md) -- its three phases are serialised by CTA barriers because the centroid fragments leave no
+    // registers for a producer/consumer role split.
+    if (N > 0 && !inertia && (flags & KP_MMA) && kmeans_mma_supported(K, D)) {
+        rc = launch_kmeans_mma(K, x_sorted, class_off, N, D, C, centroid, cnorm, assign, ws_sum, ws_cnt, G, pdl, st);
+        if (rc) return rc;
+    } else if (N > 0 && !inertia && K >= K2_MINK && K <= K2_MAXK) {
 #define DD_KP(KK) case KK: rc = launch_kmeans_pair<KK>(x_sorted, class_off, N, D, C, centroid, cnorm, assign, ws_sum, ws_cnt, G, pdl, st); break;
         switch (K) { DD_KP(4) DD_KP(5) DD_KP(6) DD_KP(7) DD_KP(8) DD_KP(9) DD_KP(10) }
 #undef DD_KP
@@ -1000,9 +976,10 @@ int dd_kmeans_update(const double* sum, const int64_t* cnt, int C, int K, int D,
 
 int dd_kmeans_assign_accum(const float* x_sorted, const int64_t* class_off, int64_t N, int D, int C, int K,
                            const float* centroid, const float* cnorm, int32_t* assign, double* sum, int64_t* cnt,
-                           double* inertia, void* ws, size_t ws_bytes, dd_stream_t stream) {
-    return dd::kmeans_pass(x_sorted, class_off, N, D, C, K, centroid, cnorm, assign, sum, cnt, inertia, ws, ws_bytes, 0,
-                           (cudaStream_t)stream);
+                           double* inertia, void* ws, size_t ws_bytes, int flags, dd_stream_t stream) {
+    DD_REQUIRE((flags & ~1) == 0, DD_EINVAL, "dd_kmeans_assign_accum: flags %d (bit 0: tensor-core kernel for K = 4..10)", flags);
+    return dd::kmeans_pass(x_sorted, class_off, N, D, C, K, centroid, cnorm, assign, sum, cnt, inertia, ws, ws_bytes,
+                           (flags & 1) ? dd::KP_MMA : 0, (cudaStream_t)stream);
 }
 
 }  // extern "C"

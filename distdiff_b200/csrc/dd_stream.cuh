@@ -64,6 +64,37 @@ __device__ __forceinline__ void take_batch(const OffT* __restrict__ off, int64_t
     row += n;
 }
 
+__device__ __forceinline__ void store_f64x4(double* dst, double a, double b, double c, double d) {
+    reinterpret_cast<double2*>(dst)[0] = make_double2(a, b);
+    reinterpret_cast<double2*>(dst)[1] = make_double2(c, d);
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// Programmatic dependent launch: everything before pdl_wait() (barrier init, class lookup, the first TMA loads of the
+// constant feature rows) overlaps the tail of the previous kernel on the stream; nothing that kernel wrote may be read
+// -- and nothing it still reads may be written -- before it.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// acc[k] += row, k CTA-uniform: a binary tree of uniform branches (<= 4 levels) instead of a jump table
+// (the table costs a constant-bank load + indirect branch on the critical path of every row)
+template <int K, int LO, int HI>
+__device__ __forceinline__ void acc_add(f32x2_t (&acc)[K][4], int k, const float4& a, const float4& b) {
+    if constexpr (HI - LO == 1) {
+        acc[LO][0] = fadd2_s(acc[LO][0], a.x, a.y);
+        acc[LO][1] = fadd2_s(acc[LO][1], a.z, a.w);
+        acc[LO][2] = fadd2_s(acc[LO][2], b.x, b.y);
+        acc[LO][3] = fadd2_s(acc[LO][3], b.z, b.w);
+    } else {
+        constexpr int MID = (LO + HI) / 2;
+        if (k < MID) acc_add<K, LO, MID>(acc, k, a, b);
+        else acc_add<K, MID, HI>(acc, k, a, b);
+    }
+}
+
 // ---- fixed-order reduction of the per-(CTA, class) partial slots a streaming pass leaves in its workspace ----
 // CTA g of G owns rows [N g / G, N (g+1) / G) and stores its partial of class c in slot (g + c) (unique: CTA ranges
 // and classes are both ordered).  A 256-thread CTA adds the slots of row (c, k) in ascending g -- the one order used

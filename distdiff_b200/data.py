@@ -43,6 +43,9 @@ class SyntheticCaltech(data.Dataset):
         img = (0.5 * base + 0.5 * np.kron(low, np.ones((8, 8, 1)))).astype(np.uint8)   # blocky, class-tinted
         return Image.fromarray(img, "RGB")
 
+    def size(self, idx):
+        return self.hw[1], self.hw[0]                                          # (w, h) like PIL
+
     def __getitem__(self, idx):
         img = self.image(idx)
         if self.transform is not None:
@@ -71,6 +74,14 @@ class ImageFolderSorted(data.Dataset):
         image = exif_transpose(Image.open(self.paths[idx]))                    # dataloader.py:79-82
         return image if image.mode == "RGB" else image.convert("RGB")
 
+    def size(self, idx):
+        """(w, h) as ``image(idx).size`` would report, from the file header only (no pixel decode)."""
+        with Image.open(self.paths[idx]) as im:
+            w, h = im.size
+            if im.getexif().get(0x0112) in (5, 6, 7, 8):                       # EXIF orientations that swap the axes
+                w, h = h, w
+        return w, h
+
     def __getitem__(self, idx):
         img = self.image(idx)
         if self.transform is not None:
@@ -90,72 +101,101 @@ class SDDataset(data.Dataset):
     embedding (stored under the reference's key names), the label, class name and image path."""
 
     def __init__(self, args, text_embed_fn, vae, size=512, device="cuda", latent_dtype=torch.float32, only=None):
-        """``only``: indices this process will read (its ``--split`` block).  Used only with ``args.shard_latents``:
-        the VAE encode then covers just those images, each with its own generator seeded by (seed, index), so the
-        latents do not depend on how the set is split -- but they are NOT the reference's draws (the reference encodes
-        the whole set in every process from one sequential RNG stream, dataloader.py:798-811), hence opt-in."""
+        """``only``: indices this process will read (its ``--split`` block): the VAE encode then covers just those images
+        (the reference encodes the whole set in every process, dataloader.py:798-811), while the two RNG
+        streams are advanced through the skipped images exactly as a full encode would -- the block's latents equal the
+        single-process ones bit for bit."""
         from torchvision import transforms
         self.args = args
         self.base = load_trainset(args, None)
         self.class_names = self.base.class_names
         self.size = size
-        center_crop = bool(getattr(args, "center_crop", False))                # dataloader.py:757-764
+        center_crop = self.center_crop = bool(getattr(args, "center_crop", False))   # dataloader.py:757-764
         self.tf = transforms.Compose([transforms.Resize(size, interpolation=transforms.InterpolationMode.BILINEAR),
                                       transforms.CenterCrop(size) if center_crop else transforms.RandomCrop(size),
                                       transforms.ToTensor(), transforms.Normalize([0.5], [0.5])])
         self.prompt_embeds = [text_embed_fn(PROMPT_TEMPLATE.format(n)) for n in self.class_names]
         self.uncond_embeds = text_embed_fn("")
-        if getattr(args, "shard_latents", False):
-            self.image_latents = self._latents_sharded(vae, device, latent_dtype, range(len(self.base)) if only is None else only)
-        else:
-            self.image_latents = self._latents(vae, device, latent_dtype)
+        self.image_latents = self._latents(vae, device, latent_dtype, only)
 
     def _cache_path(self):
         model_id = str(getattr(self.args, "pretrained_model_name_or_path", "random-init")).replace("/", "--")
         return os.path.join("save", "vae_embedding", str(self.args.dataset), model_id, "image_latents.pt")
 
-    @torch.no_grad()
-    def _latents(self, vae, device, dtype) -> List[torch.Tensor]:
-        path = self._cache_path()
-        if getattr(self.args, "cache_latents", False) and os.path.exists(path):
-            return torch.load(path, map_location="cpu")
-        out = []
-        bs = 16
-        for i in range(0, len(self.base), bs):
-            imgs = torch.stack([self.tf(self.base.image(j)) for j in range(i, min(i + bs, len(self.base)))]).to(device)
-            z = vae.encode(imgs.to(next(vae.parameters()).dtype)).latent_dist.sample() * vae.config.scaling_factor  # :808
-            out.extend(t[None].to("cpu", dtype) for t in z)
-        if getattr(self.args, "cache_latents", False):
-            os.makedirs(os.path.dirname(path), exist_ok=True)
-            tmp = f"{path}.tmp{os.getpid()}"
-            torch.save(out, tmp)
-            os.replace(tmp, path)
-        return out
+    # ---- the reference's draw order (dataloader.py:798-811), image by image: the crop position from the CPU global
+    # generator (RandomCrop), then the posterior noise randn([1,4,h,w]) from the DEVICE's default generator
+    # (latent_dist.sample()).  Both streams are consumed for EVERY image of the set in order; an image outside this
+    # process's block only advances the two generators (header-only size probe, no decode, no encode), so the latents of
+    # a block are bit-identical to the ones a single process computes for the whole set.
+    def _resized_hw(self, j):
+        w, h = self.base.size(j)                                               # PIL convention (w, h), EXIF orientation applied
+        short, long_ = (w, h) if w <= h else (h, w)
+        new_short, new_long = self.size, int(self.size * long_ / short)        # transforms.Resize(int): smaller edge -> size
+        return (new_long, new_short) if w <= h else (new_short, new_long)      # (h, w)
+
+    def _skip_draws(self, j, device, wdt):
+        from torchvision import transforms
+        if not self.center_crop:
+            h, w = self._resized_hw(j)
+            transforms.RandomCrop.get_params(torch.empty(3, h, w), (self.size, self.size))
+        torch.randn(1, 4, self.size // 8, self.size // 8, device=device, dtype=wdt)
 
     @torch.no_grad()
-    def _latents_sharded(self, vae, device, dtype, indices) -> List[Optional[torch.Tensor]]:
-        """Encode only ``indices`` (no P-fold redundant encode under --total_split P).  Crop position
-        and posterior noise of image j come from generators seeded by (seed, j): split-invariant by construction."""
-        out: List[Optional[torch.Tensor]] = [None] * len(self.base)
-        seed = int(getattr(self.args, "seed", 0) or 0)
-        idx = [int(j) for j in indices]
-        bs = 16
+    def _latents(self, vae, device, dtype, only=None) -> List[Optional[torch.Tensor]]:
+        path = self._cache_path()
+        cache = bool(getattr(self.args, "cache_latents", False))
+        if cache and os.path.exists(path):
+            return torch.load(path, map_location="cpu")
+        n = len(self.base)
+        want = None if only is None else set(int(j) for j in only)
+        out: List[Optional[torch.Tensor]] = [None] * n
         wdt = next(vae.parameters()).dtype
-        for i in range(0, len(idx), bs):
-            chunk = idx[i:i + bs]
-            imgs = []
-            for j in chunk:
-                state = torch.random.get_rng_state()
-                torch.manual_seed(seed * 1_000_003 + j)                       # RandomCrop draws from the global CPU generator
-                imgs.append(self.tf(self.base.image(j)))
-                torch.random.set_rng_state(state)
-            moments = vae.encode(torch.stack(imgs).to(device, wdt)).latent_dist
-            for k, j in enumerate(chunk):
-                g = torch.Generator(device="cpu").manual_seed(seed * 1_000_003 + 7919 + j)
-                noise = torch.randn(moments.mean[k].shape, generator=g).to(device, moments.mean.dtype)
-                z = (moments.mean[k] + moments.std[k] * noise) * vae.config.scaling_factor
-                out[j] = z[None].to("cpu", dtype)
+        sf = vae.config.scaling_factor
+        pend = []
+
+        def flush():
+            if not pend:
+                return
+            dist_ = vae.encode(torch.stack([im for _, im, _ in pend]).to(device, wdt)).latent_dist     # batched encoder forward
+            for k, (j, _im, noise) in enumerate(pend):
+                out[j] = ((dist_.mean[k:k + 1] + dist_.std[k:k + 1] * noise) * sf).to("cpu", dtype)      # :808-809
+            pend.clear()
+
+        for j in range(n):
+            if want is not None and j not in want:
+                self._skip_draws(j, device, wdt)
+                continue
+            img = self.tf(self.base.image(j))                                   # crop draw (CPU generator)
+            noise = torch.randn(1, 4, img.shape[1] // 8, img.shape[2] // 8, device=device, dtype=wdt)   # posterior draw (device generator)
+            pend.append((j, img, noise))
+            if len(pend) == 16:
+                flush()
+        flush()
+        if cache and want is None:
+            self.save_cache(out)
         return out
+
+    def save_cache(self, latents) -> None:
+        """Atomic write of the complete list in the reference's layout (dataloader.py:788-796)."""
+        if any(t is None for t in latents):
+            raise ValueError("image_latents.pt must hold every image of the set")
+        path = self._cache_path()
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        tmp = f"{path}.tmp{os.getpid()}"
+        torch.save(list(latents), tmp)
+        os.replace(tmp, path)
+
+    def merge_blocks(self, gather_object, rank: int):
+        """torchrun: every rank encoded its own block; ``gather_object(obj) -> [obj per rank]`` (e.g.
+        torch.distributed.all_gather_object) merges them, rank 0 publishes the cache file.  Returns the full list."""
+        mine = {j: t for j, t in enumerate(self.image_latents) if t is not None}
+        full = list(self.image_latents)
+        for blk in gather_object(mine):
+            for j, t in blk.items():
+                full[j] = t
+        if rank == 0 and getattr(self.args, "cache_latents", False):
+            self.save_cache(full)
+        return full
 
     def __len__(self):
         return len(self.base)
@@ -163,7 +203,7 @@ class SDDataset(data.Dataset):
     def __getitem__(self, idx):
         y = self.base.targets[idx]
         if self.image_latents[idx] is None:
-            raise IndexError(f"image {idx} is outside the block this process encoded (--shard_latents)")
+            raise IndexError(f"image {idx} is outside the block this process encoded (its --split block)")
         return {"image_latents": self.image_latents[idx], "instance_prompt_ids": self.prompt_embeds[y],
                 "uncond_inputs_ids": self.uncond_embeds, "targets": y, "class_names": self.class_names[y],
                 "image_paths": self.base.paths[idx]}

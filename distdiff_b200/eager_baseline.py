@@ -20,8 +20,17 @@ launch_count = 0   # not tracked for ATen launches (bench.py reports the profile
 profiler = None
 
 
+_scalars = {}
+
+
 def _dev_scalar(v, ref):
-    return torch.tensor(float(v), dtype=torch.float32, device=ref.device)
+    """0-dim fp32 device tensor holding ``v`` -- diffusers indexes a device-resident alphas_cumprod table, which costs no
+    host-to-device copy; cached so that the same holds here (and under CUDA-graph capture, after the warm-up runs)."""
+    key = (float(v), ref.device)
+    t = _scalars.get(key)
+    if t is None:
+        t = _scalars[key] = torch.tensor(float(v), dtype=torch.float32, device=ref.device)
+    return t
 
 
 # ---- K5: CFG combine + DDIMScheduler.step (eta = 0, epsilon prediction) ------------------------------------------

@@ -60,9 +60,73 @@ class _GraphedStep:
         return self.out_prev.clone(), self.out_x0
 
 
+class _GraphedGuidance:
+    """transform_guidance's device work -- ChannelAffine, `period` x (UNet fwd, K5, VAE decode, K8, guide, K4), the autograd
+    backward through all of it, the parameter update and the projected transform -- captured once per (timesteps, batch
+    shape) in a CUDA graph.  Only the two CPU RNG draws of the channel parameters (generate_data.py:692-695, reference
+    order) and three small copies into static buffers happen per call; the guided step is otherwise launch-by-launch
+    (~2.5k launches at B = 8)."""
+
+    def __init__(self, expander, latents, prompt_embeds, targets, guide_ts):
+        dev = latents.device
+        bs, ch = latents.shape[0], latents.shape[1]
+        self.static_lat = latents.clone()
+        self.static_prompt = prompt_embeds.clone()
+        self.static_targets = targets.clone()
+        self.static_cn = torch.zeros(bs, ch, 1, 1, device=dev)
+        self.static_cb = torch.zeros(bs, ch, 1, 1, device=dev)
+        ts = [int(t) for t in guide_ts]
+        e = expander
+
+        def run():
+            # the timestep is a python int here: the UNet builds its embedding on the device (no H2D inside the capture
+            # because nets.UNet2DConditionModel takes the device tensor below) and the scheduler tables are host floats
+            return guidance.transform_guidance_core(self.static_lat, self.static_targets, self.static_cn, self.static_cb,
+                                                    [self._t(t, dev) for t in ts], e.sched, e.unet, self.static_prompt, None, e.vae,
+                                                    e.image_encoder, e.image_processor, None, e.gproto, e.lproto)
+        self._tcache = {}
+        for t in ts:
+            self._t(t, dev)
+        self.graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):   # warm-up outside capture (cuDNN autotune for the backward convs, workspaces)
+                run()
+        torch.cuda.current_stream().wait_stream(side)
+        with torch.cuda.graph(self.graph, pool=expander._graph_pool):
+            self.out_lat, self.out_score = run()
+
+    def _t(self, t, dev):
+        v = self._tcache.get(t)
+        if v is None:
+            v = self._tcache[t] = _DevTimestep(t, dev)
+        return v
+
+    def __call__(self, latents, prompt_embeds, targets, channel_noise, channel_noise_bias):
+        self.static_lat.copy_(latents)
+        self.static_prompt.copy_(prompt_embeds)
+        self.static_targets.copy_(targets)
+        self.static_cn.copy_(channel_noise, non_blocking=True)
+        self.static_cb.copy_(channel_noise_bias, non_blocking=True)
+        self.graph.replay()
+        return self.out_lat.clone(), self.out_score.clone()
+
+
+class _DevTimestep(int):
+    """A timestep that is an int for the scheduler tables (``int(t)``) and carries a device tensor for the UNet, so no
+    host-to-device copy is issued while a graph is being captured."""
+
+    def __new__(cls, t, dev):
+        obj = super().__new__(cls, int(t))
+        obj.dev = torch.full((1,), int(t), dtype=torch.int64, device=dev)
+        return obj
+
+
 class Expander:
     def __init__(self, args, unet, vae, image_encoder, image_processor, noise_scheduler: DDIMScheduler,
-                 total_global_proto, total_local_proto, weight_dtype=torch.float16, device="cuda", use_cuda_graph=False):
+                 total_global_proto, total_local_proto, weight_dtype=torch.float16, device="cuda", use_cuda_graph=False,
+                 graph_guidance=True):
         self.args = args
         guidance.set_args(args)
         self.unet, self.vae, self.image_encoder, self.image_processor = unet, vae, image_encoder, image_processor
@@ -72,6 +136,7 @@ class Expander:
         self.device = torch.device(device)
         self.timesteps, _ = retrieve_timesteps(noise_scheduler, NUM_INFERENCE_STEPS, "cpu")   # :1043-1044
         self.use_cuda_graph = use_cuda_graph
+        self.graph_guidance = bool(graph_guidance)
         self._graphs = {}
         self._graph_pool = torch.cuda.graph_pool_handle() if use_cuda_graph else None
 
@@ -97,6 +162,18 @@ class Expander:
         if g is None:
             g = self._graphs[key] = _GraphedStep(self, latents, prompt_embeds, t)
         return g(latents, prompt_embeds)
+
+    def _guided(self, latents, prompt_embeds, batch, guide_ts):
+        """transform_guidance through a captured graph: the CPU draws stay in the reference's order, everything else replays."""
+        cn, cb = guidance.draw_channel_noise(latents.shape[0], latents.shape[1])
+        C_ = (self.gproto if self.gproto is not None else self.lproto).shape[0]
+        targets = ops.targets_tensor(batch["targets"], C_, latents.device)
+        key = ("guided", tuple(int(t) for t in guide_ts), tuple(latents.shape), latents.dtype)
+        g = self._graphs.get(key)
+        if g is None:
+            g = self._graphs[key] = _GraphedGuidance(self, latents, prompt_embeds, targets, guide_ts)
+        ops.launch_count += 2 * len(guide_ts) + 4   # K6 fwd/bwd + per sub-step (K5 fwd/bwd, K8 fwd/bwd, K4) + K6 project, replayed
+        return g(latents, prompt_embeds, targets, cn.pin_memory(), cb.pin_memory())
 
     def expand_batch(self, batch, image_i: int = 0, decode: bool = True, as_uint8: bool = False):
         """generate_data.py:1145-1227 for one batch -> (images [B,3,H,W] in [0,1] or None, latents, info).
@@ -124,9 +201,12 @@ class Expander:
         logger.info("Guidance timesteps: %s", ", ".join(str(x) for x in guide_ts))
         for t in timesteps[start_index:]:                                                  # :1199
             if t == guide_ts[0] and a.guidance_type == "transform_guidance":
-                latents, score = guidance.transform_guidance(latents, batch, guide_ts, self.sched, self.unet, prompt_embeds,
-                                                             None, self.vae, self.image_encoder, self.image_processor, wd,
-                                                             generator, self.gproto, self.lproto)
+                if self.use_cuda_graph and self.graph_guidance:
+                    latents, score = self._guided(latents, prompt_embeds, batch, guide_ts)
+                else:
+                    latents, score = guidance.transform_guidance(latents, batch, guide_ts, self.sched, self.unet, prompt_embeds,
+                                                                 None, self.vae, self.image_encoder, self.image_processor, wd,
+                                                                 generator, self.gproto, self.lproto)
                 latents, x_0 = self._step(latents, prompt_embeds, t)
                 info["scores"].append(score)       # no .item(): the reference syncs here every guided step (:1208)
             elif int(t) in guide_ts and a.guidance_type == "direct_guidance":

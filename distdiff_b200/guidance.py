@@ -71,16 +71,21 @@ def _guide_features(pred_x0, vae, image_encoder, image_processor, generator):
     return image_encoder.encode_image(D_x0_t).float()
 
 
-def transform_guidance(latents, batch, sub_timesteps, noise_scheduler, unet, prompt_embeds, class_labels,
-                       vae, image_encoder, image_processor, weight_dtype, generator,
-                       total_global_proto, total_local_proto):
-    """generate_data.py:687-732 -> (latents, score)."""
+def draw_channel_noise(bs: int, channel_noise_dim: int):
+    """generate_data.py:692-695 -- CPU global RNG, rand first then normal_ (host tensors; the caller moves them)."""
+    channel_noise = torch.rand([bs, channel_noise_dim, 1, 1])
+    channel_noise_bias = torch.zeros([bs, channel_noise_dim, 1, 1]).normal_(0, 1)
+    return channel_noise, channel_noise_bias
+
+
+def transform_guidance_core(latents, targets, channel_noise, channel_noise_bias, sub_timesteps, noise_scheduler, unet,
+                            prompt_embeds, class_labels, vae, image_encoder, image_processor, generator,
+                            total_global_proto, total_local_proto):
+    """generate_data.py:696-732 given the drawn channel parameters (device fp32 leaves).  Shape-static and free of host
+    synchronisation, so expand.Expander can capture it -- forward, autograd backward and the update -- in a CUDA graph."""
     a = _need_args()
-    bs = latents.shape[0]
-    channel_noise_dim = latents.shape[1]
-    # :692-695 -- CPU global RNG, rand first then normal_; kept as fp32 leaves (the reference rounds them to fp16)
-    channel_noise = torch.rand([bs, channel_noise_dim, 1, 1]).to(latents.device).requires_grad_(True)
-    channel_noise_bias = torch.zeros([bs, channel_noise_dim, 1, 1]).normal_(0, 1).to(latents.device).requires_grad_(True)
+    channel_noise = channel_noise.detach().requires_grad_(True)
+    channel_noise_bias = channel_noise_bias.detach().requires_grad_(True)
     latents = latents.detach()
     x_dec_noisy = ops.ChannelAffine.apply(latents, channel_noise, channel_noise_bias)          # :696
 
@@ -88,7 +93,7 @@ def transform_guidance(latents, batch, sub_timesteps, noise_scheduler, unet, pro
     for temp_t in sub_timesteps:
         x_dec_noisy, pred_x0 = denoise_one_step(x_dec_noisy, noise_scheduler, temp_t, unet, prompt_embeds, class_labels)
         image_features = _guide_features(pred_x0, vae, image_encoder, image_processor, generator)
-        score = score + ops.PrototypeEnergy.apply(image_features, batch["targets"], total_global_proto, total_local_proto,
+        score = score + ops.PrototypeEnergy.apply(image_features, targets, total_global_proto, total_local_proto,
                                                   float(a.gs), float(a.ls), False)            # :707-717
     score = score / a.guidance_period
 
@@ -99,6 +104,17 @@ def transform_guidance(latents, batch, sub_timesteps, noise_scheduler, unet, pro
     # :726-728 -- transform again with the updated params and project onto the L-inf ball around the input
     latents = ops.affine_project(latents, channel_noise.data, channel_noise_bias.data, float(a.constraint_value))
     return latents.detach(), score.detach()
+
+
+def transform_guidance(latents, batch, sub_timesteps, noise_scheduler, unet, prompt_embeds, class_labels,
+                       vae, image_encoder, image_processor, weight_dtype, generator,
+                       total_global_proto, total_local_proto):
+    """generate_data.py:687-732 -> (latents, score)."""
+    # :692-695 -- CPU global RNG, rand first then normal_; kept as fp32 leaves (the reference rounds them to fp16)
+    channel_noise, channel_noise_bias = draw_channel_noise(latents.shape[0], latents.shape[1])
+    return transform_guidance_core(latents, batch["targets"], channel_noise.to(latents.device), channel_noise_bias.to(latents.device),
+                                   sub_timesteps, noise_scheduler, unet, prompt_embeds, class_labels, vae, image_encoder,
+                                   image_processor, generator, total_global_proto, total_local_proto)
 
 
 def direct_guidance(latents, batch, t_i, noise_scheduler, unet, prompt_embeds, class_labels,

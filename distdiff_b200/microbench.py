@@ -7,7 +7,7 @@ every timed launch by READING a 512 MB buffer (a write-flush would leave dirty l
 bandwidth from the timed kernel), CUDA events on the launching stream, median of ``iters``.
 
 Algorithmic bytes per launch:
-  K5 fwd/bwd 5*B*16384*s   K6 2*B*16384*s   K7 3*B*16384*s   K4 2*B*D*4+(K+1)*C*D*4 (compulsory HBM bytes)   K1 2*N*D*4+N*8   K3 N*D*4+2*N*4   K8 (B*3*512*512 + B*3*224*224)*s   K9 B*3*512*512*(s+1)
+  K5 fwd/bwd 5*B*16384*s   K6 2*B*16384*s   K7 3*B*16384*s   K4 2*B*D*4+(K+1)*min(B,C)*D*4 (compulsory HBM bytes)   K1 2*N*D*4+N*8   K3 N*D*4+2*N*4   K8 (B*3*512*512 + B*3*224*224)*s   K9 B*3*512*512*(s+1)
 """
 from __future__ import annotations
 
@@ -120,7 +120,7 @@ def run(want=lambda name: True, iters=10, ks=(3, 5, 10), latent_dtypes=(torch.fl
                 y = torch.randint(0, C, (B,), device=dev)
                 # bytes = compulsory HBM traffic (f read + grad written + the tables once); SURVEY's B*(K+3)*D*4 counts
                 # the per-sample prototype reads, which are L2 hits (tables <= 8 MB) -- kept as survey_bytes only
-                nbytes = 2 * B * D * 4 + (K + 1) * C * D * 4
+                nbytes = 2 * B * D * 4 + (K + 1) * min(B, C) * D * 4
                 for nf in (False, True):
                     for mode in (("auto",) if B < 1024 else ("sample", "tile")):
                         t = timeit(lambda: ops.energy_fwd_bwd(f, y, g, l, 1.0, 1.0, nf, mode=mode), iters)
@@ -176,6 +176,8 @@ def run(want=lambda name: True, iters=10, ks=(3, 5, 10), latent_dtypes=(torch.fl
             s, c = ops.kmeans_seed(xs, idx.contiguous())
             ops.kmeans_update(s, c, buf.centroid, buf.cnorm)
             report(f"K3_kmeans_assign_accum_N{N}_K{K}", N * D * 4 + 2 * N * 4, timeit(lambda: ops.kmeans_assign_accum(xs, off, buf), iters))
+            if 4 <= K <= 10:   # the tensor-core variant (opt-in): same pass with split-fp16 mma.sync dot products
+                report(f"K3_kmeans_assign_accum_mma_N{N}_K{K}", N * D * 4 + 2 * N * 4, timeit(lambda: ops.kmeans_assign_accum(xs, off, buf, mma=True), iters))
             if want("eager") and K in (3, 10):   # one Lloyd iteration as centroid gather + cdist + argmin + index_add_
                 row_class = torch.repeat_interleave(torch.arange(C, device=dev), off[1:] - off[:-1])
                 report(f"eager_K3_kmeans_iteration_N{N}_K{K}", N * D * 4 + 2 * N * 4,

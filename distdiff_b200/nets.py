@@ -159,7 +159,10 @@ class UNet2DConditionModel(nn.Module):
         return fn(*a)
 
     def forward(self, sample, timestep, encoder_hidden_states, class_labels=None, return_dict=False):
-        t = torch.as_tensor(timestep, device=sample.device).reshape(-1)
+        t = getattr(timestep, "dev", None)       # expand._DevTimestep: an int that already carries its device tensor (graph capture)
+        if t is None:
+            t = torch.as_tensor(timestep, device=sample.device)
+        t = t.reshape(-1)
         if t.numel() == 1:
             t = t.expand(sample.shape[0])
         temb = self.time_embedding(timestep_embedding(t, self._ch0, sample.dtype))

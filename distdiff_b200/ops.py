@@ -473,16 +473,19 @@ class KMeansBuffers:
         return C_ * K * (D * 12 + 20) + 5 * 256
 
 
-def kmeans_assign_accum(x_sorted: torch.Tensor, class_off: torch.Tensor, buf: KMeansBuffers, want_inertia: bool = False) -> None:
+def kmeans_assign_accum(x_sorted: torch.Tensor, class_off: torch.Tensor, buf: KMeansBuffers, want_inertia: bool = False,
+                        mma: bool = False) -> None:
     """K3: one assignment + accumulation pass; results land in buf.assign / buf.sum / buf.cnt (and buf.inertia when
-    ``want_inertia``: that variant reduces one more value per row, so fewer rows share a reduction round)."""
+    ``want_inertia``: that variant reduces one more value per row, so fewer rows share a reduction round).
+    ``mma``: K = 4..10 with the dot products on the tensor cores (split-fp16 mma.sync; same assignments, measured slower
+    than the default FMA-pipe kernel -- kept as the measured alternative)."""
     x_sorted = _req(x_sorted, "x_sorted", torch.float32)
     N, D = x_sorted.shape
     Cn, K, _ = buf.centroid.shape
     _call("dd_kmeans_assign_accum", N * D * 4 + 2 * N * 4, 2 if want_inertia else 1,
           _ptr(x_sorted), _ptr(class_off), N, D, Cn, K, _ptr(buf.centroid), _ptr(buf.cnorm),
                                             _ptr(buf.assign), _ptr(buf.sum), _ptr(buf.cnt), _ptr(buf.inertia) if want_inertia else None, _ptr(buf.ws),
-                                            buf.ws.numel(), _stream())
+                                            buf.ws.numel(), int(bool(mma)), _stream())
 
 
 def kmeans_lloyd(x_sorted: torch.Tensor, class_off: torch.Tensor, buf: KMeansBuffers, iters: int, comm=None) -> None:

@@ -71,8 +71,7 @@ def parse_args(input_args=None):
     p.add_argument("--synthetic_per_class", type=int, default=30)
     p.add_argument("--cuda_graph", action="store_true", help="replay the unguided step (UNet + K5) from a CUDA graph")
     p.add_argument("--cache_latents", action="store_true", help="persist save/vae_embedding/.../image_latents.pt like the reference")
-    p.add_argument("--shard_latents", action="store_true",
-                   help="VAE-encode only this split's images, with per-image generators (split-invariant, but not the reference's RNG draws)")
+    p.add_argument("--shard_latents", action="store_true", help="(default behaviour now; kept for compatibility)")
     p.add_argument("--tiny_models", action="store_true", help="tiny random-init UNet/VAE/guide (tests)")
     p.add_argument("--max_batches", type=int, default=None, help="stop after this many batches (smoke runs)")
     args, unknown = p.parse_known_args(input_args)
@@ -160,11 +159,22 @@ def main(args):
     # (deterministic per class name); images are NOT comparable with the reference's until a real text encoder is plugged
     # in here.  Everything downstream of the embeddings is the reference's computation.
     embed = dd_data.random_text_embedder()
-    only = None
-    if args.shard_latents:      # opt-in: encode only this process's block (per-image generators; not the reference's draws)
-        only = guidance.split_mask(len(dd_data.load_trainset(args, None)), args.split, args.total_split)
+    # Every process VAE-encodes only its own --split block (the reference re-encodes the whole set per process,
+    # dataloader.py:798-811); the RNG streams are advanced through the skipped images, so the block's latents are the
+    # single-process ones bit for bit.  A complete image_latents.pt (--cache_latents) is written by a single process
+    # (total_split 1) or, under torchrun, by rank 0 after the blocks are gathered.
+    n_images = len(dd_data.load_trainset(args, None))
+    mask = guidance.split_mask(n_images, args.split, args.total_split)
+    only = mask if (args.total_split > 1 and (world > 1 or not args.cache_latents)) else None
     dataset = dd_data.SDDataset(args, embed, vae, size=512 if not args.tiny_models else 64, device=device, only=only)
-    mask = guidance.split_mask(len(dataset), args.split, args.total_split)
+    if world > 1 and args.cache_latents and only is not None:
+        import torch.distributed as dist
+
+        def gather(obj):
+            box = [None] * world
+            dist.all_gather_object(box, obj)
+            return box
+        dataset.merge_blocks(gather, rank)
     loader = DataLoader(Subset(dataset, mask), batch_size=args.train_batch_size, shuffle=False,
                         collate_fn=dd_data.collate_fn, num_workers=args.dataloader_num_workers, drop_last=False)
 

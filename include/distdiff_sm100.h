@@ -149,10 +149,14 @@ int dd_normalize_rows(const float* in, int64_t R, int D, float* out, dd_stream_t
 int dd_kmeans_seed(const float* x_sorted, const int64_t* row_idx, int64_t R, int D, double* sum, int64_t* cnt,
                    dd_stream_t stream);
 /* assign[i] = argmin_k (cnorm[c,k] - 2 <x_i, centroid[c,k]>) (lowest k on ties), sum[c,k] += x_i (fp64),
- * cnt[c,k] += 1, inertia += ||x_i - centroid[c,k*]||^2.  sum/cnt/inertia are overwritten (not accumulated). */
+ * cnt[c,k] += 1, inertia += ||x_i - centroid[c,k*]||^2.  sum/cnt/inertia are overwritten (not accumulated).
+ * flags: bit 0 = (K = 4..10, D % 256 == 0, no inertia) run the K dot products per row on the tensor cores: mma.sync, both
+ * operands split into fp16 hi + lo parts, three MMAs per step, error ~3e-6 ||x|| ||mu|| -- fp32-grade, the assignment is
+ * the fp32 one up to the documented ties (top-2 score gap <= 1e-5).  Opt-in: measured slower than the default FMA-pipe
+ * kernel on B200. */
 int dd_kmeans_assign_accum(const float* x_sorted, const int64_t* class_off, int64_t N, int D, int C, int K,
                            const float* centroid, const float* cnorm, int32_t* assign, double* sum, int64_t* cnt,
-                           double* inertia, void* ws, size_t ws_bytes, dd_stream_t stream);
+                           double* inertia, void* ws, size_t ws_bytes, int flags, dd_stream_t stream);
 /* centroid[c,k] = fp32(sum/cnt) where cnt > 0 (an empty cluster keeps its centroid); cnorm = ||centroid||^2. */
 int dd_kmeans_update(const double* sum, const int64_t* cnt, int C, int K, int D, float* centroid, float* cnorm,
                      dd_stream_t stream);

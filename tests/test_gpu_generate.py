@@ -46,7 +46,8 @@ def test_cuda_graph_step_matches_eager(cuda_device, tmp_path, monkeypatch):
     monkeypatch.chdir(tmp_path)
     args = gd.parse_args(COMMON + ["--output_dir", "o"])
     args.optimize_targets = None
-    unet, vae, guide = gd.build_models(args, cuda_device, torch.float32)
+    unet, vae = gd.build_models(args, cuda_device, torch.float32)
+    guide = gd.build_guide(args, args.synthetic_classes, cuda_device)
     batch = {"input_ids": torch.randn(2, 77, 768), "uncond_inputs_ids": torch.randn(2, 77, 768),
              "image_latents": torch.randn(2, 4, 8, 8), "targets": [0, 1], "class_names": ["a", "b"], "image_paths": ["x.jpg", "y.jpg"]}
     outs = []
@@ -60,6 +61,49 @@ def test_cuda_graph_step_matches_eager(cuda_device, tmp_path, monkeypatch):
     assert outs[0][0].min() >= 0 and outs[0][0].max() <= 1
 
 
+def test_cuda_graph_guided_step_matches_eager(cuda_device, tmp_path, monkeypatch):
+    """transform_guidance captured in a CUDA graph (forward, autograd backward, update, projection) == the eager call:
+    same CPU RNG draws, same latents and scores; a second batch replays the same graph with new inputs."""
+    import generate_data as gd
+    from distdiff_b200 import expand, nets, ops
+    from distdiff_b200.scheduler import DDIMScheduler
+    monkeypatch.chdir(tmp_path)
+    # fp32 convolutions without TF32: cuDNN may pick different algorithms inside a capture, and TF32 rounding differences in
+    # the gradient are amplified by rho = 10 in the channel-parameter update
+    monkeypatch.setattr(torch.backends.cudnn, "allow_tf32", False)
+    monkeypatch.setattr(torch.backends.cuda.matmul, "allow_tf32", False)
+    args = gd.parse_args(COMMON + ["--output_dir", "o", "--guidance_type", "transform_guidance", "--guidance_step", "20", "--guidance_period", "2",
+                                   "--optimize_targets", "global_prototype-local_prototype", "--strength", "1.0"])
+    args.optimize_targets = args.optimize_targets.split("-")
+    unet, vae = gd.build_models(args, cuda_device, torch.float32)
+    guide = gd.build_guide(args, 6, cuda_device)
+    g = torch.Generator().manual_seed(3)
+    D = 512
+    gp = ops.normalize_rows(torch.randn(6, D, generator=g).to(cuda_device))
+    lp = ops.normalize_rows(torch.randn(6, 3, D, generator=g).to(cuda_device))
+    batches = [{"input_ids": torch.randn(2, 77, 768, generator=g), "uncond_inputs_ids": torch.randn(2, 77, 768, generator=g),
+                "image_latents": torch.randn(2, 4, 8, 8, generator=g), "targets": [i, 5 - i], "class_names": ["a", "b"],
+                "image_paths": ["x.jpg", "y.jpg"]} for i in range(2)]
+    from distdiff_b200 import guidance
+    ex = expand.Expander(args, unet, vae, guide, nets.VaeImageProcessor(), DDIMScheduler(), gp, lp,
+                         weight_dtype=torch.float32, device=cuda_device, use_cuda_graph=True)
+    guide_ts = guidance.guide_timesteps(ex.timesteps, args.guidance_step, args.guidance_period)
+    outs = []
+    for b in batches:          # the second batch REPLAYS the graph captured for the first one
+        lat = b["image_latents"].to(cuda_device)
+        prompt = torch.cat([b["uncond_inputs_ids"], b["input_ids"]]).to(cuda_device)
+        torch.manual_seed(11)
+        l_ref, s_ref = guidance.transform_guidance(lat, b, guide_ts, ex.sched, unet, prompt, None, vae, guide, ex.image_processor,
+                                                   torch.float32, None, gp, lp)
+        torch.manual_seed(11)  # same CPU draws of the channel parameters (generate_data.py:692-695)
+        l_g, s_g = ex._guided(lat, prompt, b, guide_ts)
+        assert abs(float(s_ref) - float(s_g)) <= 1e-5 * abs(float(s_ref))
+        assert (l_ref - l_g).abs().max() <= 1e-4 * l_ref.abs().max()
+        outs.append(l_g.clone())
+    assert not torch.equal(outs[0], outs[1])      # the replay really used the second batch's inputs
+    assert len([k for k in ex._graphs if k[0] == "guided"]) == 1
+
+
 def test_config5_guidance_every_step_bf16(cuda_device, tmp_path, monkeypatch):
     """BASELINE configs[4] in miniature: 1000-class prototype tables, bf16 networks, `direct_guidance` on ALL 50 steps
     (--strength 1.0 --guidance_step 50 --guidance_period 50, SURVEY section 7 'timestep-index arithmetic').  Every step
@@ -71,7 +115,8 @@ def test_config5_guidance_every_step_bf16(cuda_device, tmp_path, monkeypatch):
     base = [a for a in COMMON if a not in ("transform_guidance",)]
     args = gd.parse_args(base + ["--guidance_type", "direct_guidance", "--output_dir", "o"])
     args.strength, args.guidance_step, args.guidance_period, args.synthetic_classes = 1.0, 50, 50, 1000
-    unet, vae, guide = gd.build_models(args, cuda_device, torch.float32)
+    unet, vae = gd.build_models(args, cuda_device, torch.float32)
+    guide = gd.build_guide(args, args.synthetic_classes, cuda_device)
     g = torch.Generator().manual_seed(3)
     gproto = ops.normalize_rows(torch.randn(1000, 512, generator=g).to(cuda_device))
     lproto = ops.normalize_rows(torch.randn(1000, 2, 512, generator=g).to(cuda_device))

@@ -467,19 +467,21 @@ def test_kmeans_one_iteration_vs_oracle(ops, cuda_device, N, C, D, K):
     s1 = buf.sum.clone(); a1 = buf.assign.clone(); c1 = buf.cnt.clone()
     ops.kmeans_assign_accum(xs, off, buf, want_inertia=True)
     assert torch.equal(s1, buf.sum) and torch.equal(a1, buf.assign)
-    # the inertia-free call runs the cluster-paired kernel for K <= 10 (another summation order): same assignment
-    # except on the documented ties, counts and sums exact / to fp32 rounding for ITS OWN assignment, reproducible
-    ops.kmeans_assign_accum(xs, off, buf, want_inertia=False)
-    a2 = buf.assign.cpu().numpy()
-    assert np.array_equal(a2[clear_all], assign[clear_all])
-    for c in range(C):
-        Xc = xs_np[offc[c]:offc[c + 1]]
-        sums_ref, cnt_ref = prototypes.kmeans_sums(Xc, a2[offc[c]:offc[c + 1]], K)
-        assert np.array_equal(buf.cnt[c].cpu().numpy(), cnt_ref)
-        assert np.abs(buf.sum[c].cpu().numpy() - sums_ref).max() <= 2e-6 * (np.abs(sums_ref).max() + 1e-30)
-    s2 = buf.sum.clone(); a2t = buf.assign.clone()
-    ops.kmeans_assign_accum(xs, off, buf, want_inertia=False)
-    assert torch.equal(s2, buf.sum) and torch.equal(a2t, buf.assign)
+    # the inertia-free call runs, for K = 4..10, the cluster-paired FMA kernel or (mma=True, D % 256 == 0) the tensor-core
+    # kernel (split-fp16 MMA) -- other summation orders: same assignment except on the documented ties, counts and sums
+    # exact / to fp32 rounding for ITS OWN assignment, reproducible
+    for mma in (False, True):
+        ops.kmeans_assign_accum(xs, off, buf, want_inertia=False, mma=mma)
+        a2 = buf.assign.cpu().numpy()
+        assert np.array_equal(a2[clear_all], assign[clear_all]), mma
+        for c in range(C):
+            Xc = xs_np[offc[c]:offc[c + 1]]
+            sums_ref, cnt_ref = prototypes.kmeans_sums(Xc, a2[offc[c]:offc[c + 1]], K)
+            assert np.array_equal(buf.cnt[c].cpu().numpy(), cnt_ref)
+            assert np.abs(buf.sum[c].cpu().numpy() - sums_ref).max() <= 2e-6 * (np.abs(sums_ref).max() + 1e-30)
+        s2 = buf.sum.clone(); a2t = buf.assign.clone()
+        ops.kmeans_assign_accum(xs, off, buf, want_inertia=False, mma=mma)
+        assert torch.equal(s2, buf.sum) and torch.equal(a2t, buf.assign)
     s1 = buf.sum.clone()
     # update kernel
     old = buf.centroid.clone()

@@ -72,8 +72,10 @@ def test_image_folder_rules(tmp_path):
                 Image.fromarray(np.zeros((8, 8, 3), np.uint8)).save(root / cls / f)
     ds = data.load_trainset(types.SimpleNamespace(data_root=str(tmp_path / "data"), dataset="caltech-101"), None)
     assert ds.class_names == ["ant", "sea horse"]                               # sorted, '_' -> ' ', the two dropped classes gone
-    assert [os.path.basename(p) for p in ds.paths] == ["z.jpeg", "a.png", "b.jpg"]   # files sorted inside a class
-    assert ds.targets == [0, 1, 1]
+    # files sorted inside a class; like the reference (dataloader.py:284-286) EVERY directory entry is a sample -- a stray
+    # non-image file is a dataset error there too (PIL raises when it is opened), not something to filter silently
+    assert [os.path.basename(p) for p in ds.paths] == ["z.jpeg", "a.png", "b.jpg", "notes.txt"]
+    assert ds.targets == [0, 1, 1, 1]
 
 
 def test_synthetic_set_is_deterministic():
@@ -113,32 +115,55 @@ def test_latent_cache_layout_and_collate(tmp_path, monkeypatch):
     assert torch.equal(embed("a photo of a class 000."), ds[0]["instance_prompt_ids"])   # dataloader.py:52-62 template
 
 
-def test_sharded_latents_are_split_invariant(tmp_path, monkeypatch):
-    """--shard_latents: each split encodes only its block, with per-image generators, so the union of
-    the splits equals the unsplit run and images outside the block are refused."""
+def test_block_sharded_latents_equal_the_single_process_ones(tmp_path, monkeypatch):
+    """each --split process encodes only its block, advancing the crop / posterior RNG streams through the
+    skipped images exactly as the full encode does (dataloader.py:798-811 order), so block latents == single-process
+    latents BIT FOR BIT, images outside the block are refused, and the merged list is the reference-layout cache file."""
     from distdiff_b200 import data, guidance, nets
     monkeypatch.chdir(tmp_path)
     torch.manual_seed(0)
     vae = nets.AutoencoderKL(chs=(32, 32, 64, 64)).eval()
     args = types.SimpleNamespace(dataset="caltech-101", data_root="nowhere", synthetic_classes=3, synthetic_per_class=3, seed=42,
-                                 pretrained_model_name_or_path="x", cache_latents=False, center_crop=False, shard_latents=True)
+                                 pretrained_model_name_or_path="x", cache_latents=False, center_crop=False)
     embed = data.random_text_embedder()
+    torch.manual_seed(42)
     full = data.SDDataset(args, embed, vae, size=32, device="cpu")
     assert all(t is not None and t.shape == (1, 4, 4, 4) for t in full.image_latents)
-    torch.manual_seed(123)                                                      # the global RNG state must not matter
+    blocks = []
     for split in range(2):
         mask = guidance.split_mask(len(full), split, 2)
+        torch.manual_seed(42)                                                   # same --seed in every process (set_seed)
         part = data.SDDataset(args, embed, vae, size=32, device="cpu", only=mask)
+        blocks.append({j: t for j, t in enumerate(part.image_latents) if t is not None})
         for j in range(len(full)):
             if j in mask:
-                assert torch.allclose(part.image_latents[j], full.image_latents[j], rtol=1e-5, atol=1e-6)
+                assert torch.equal(part.image_latents[j], full.image_latents[j])
             else:
                 assert part.image_latents[j] is None
                 with pytest.raises(IndexError):
                     part[j]
-    args.seed = 43                                                              # a different --seed gives different draws
-    other = data.SDDataset(args, embed, vae, size=32, device="cpu", only=[0])
-    assert not torch.allclose(other.image_latents[0], full.image_latents[0])
+    # merge (torchrun: all_gather_object of the blocks) -> rank 0 publishes the complete cache file, atomically
+    args.cache_latents = True
+    merged = part.merge_blocks(lambda mine: blocks, rank=0)
+    assert all(torch.equal(a, b) for a, b in zip(merged, full.image_latents))
+    stored = torch.load(part._cache_path())
+    assert len(stored) == len(full) and all(torch.equal(a, b) for a, b in zip(stored, full.image_latents))
+    torch.manual_seed(43)                                                       # a different --seed gives different draws
+    other = data.SDDataset(types.SimpleNamespace(**{**vars(args), "cache_latents": False}), embed, vae, size=32, device="cpu", only=[0])
+    assert not torch.equal(other.image_latents[0], full.image_latents[0])
+
+
+def test_image_size_probe_matches_decoded_size(tmp_path):
+    from distdiff_b200 import data
+    root = tmp_path / "data" / "caltech-101" / "train" / "ant"
+    root.mkdir(parents=True)
+    Image.fromarray(np.zeros((20, 31, 3), np.uint8)).save(root / "a.png")
+    im = Image.fromarray(np.zeros((20, 31, 3), np.uint8))
+    ex = im.getexif(); ex[0x0112] = 6                                           # rotated 90 degrees: axes swap
+    im.save(root / "b.jpg", exif=ex)
+    ds = data.load_trainset(types.SimpleNamespace(data_root=str(tmp_path / "data"), dataset="caltech-101"), None)
+    for j in range(len(ds)):
+        assert ds.size(j) == ds.image(j).size
 
 
 def test_output_path_layout():
@@ -156,7 +181,7 @@ def test_cli_surface_matches_reference_flags():
     # reference defaults (generate_data.py:167-453)
     assert (a.total_split, a.split, a.num_images_per_prompt, a.K, a.guidance_scale, a.seed, a.train_batch_size) == (8, 0, 4, 3, 7.5, 42, 2)
     assert (a.strength, a.rho, a.gs, a.ls, a.constraint_value, a.guidance_step, a.guidance_period) == (0.9, 10.0, 1.0, 1.0, 0.8, 1, 1)
-    assert a.guidance_type is None and a.cluster_method == "agglomerative" and a.shard_latents is False
+    assert a.guidance_type is None and a.cluster_method == "agglomerative"
     b = gd.parse_args(["--guidance_type", "transform_guidance", "--optimize_targets", "global_prototype-local_prototype", "--K", "5",
                        "--report_to", "wandb", "--some_training_only_flag"])     # flags off the expansion path are ignored, not fatal
     assert b.guidance_type == "transform_guidance" and b.K == 5 and b.optimize_targets == "global_prototype-local_prototype"

@@ -22,6 +22,11 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr"]
 
 
+def _extra_flags():
+    """DD_EXTRA_NVCC_FLAGS: extra compile flags (e.g. -DDD_ALL_LANES_ARRIVE for the racecheck build of tools/gpu_sanitize.sh)."""
+    return os.environ.get("DD_EXTRA_NVCC_FLAGS", "").split()
+
+
 def _nvcc() -> str:
     for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if cand and os.path.exists(cand):
@@ -45,7 +50,7 @@ def _digest(paths) -> str:
     for p in sorted(paths):
         h.update(p.encode())
         h.update(open(p, "rb").read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(NVCC_FLAGS + _extra_flags()).encode())
     return h.hexdigest()
 
 
@@ -63,7 +68,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(src):
         obj = os.path.join(BUILD, os.path.basename(src)[:-3] + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-I", inc, "-c", src, "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *_extra_flags(), "-I", inc, "-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")

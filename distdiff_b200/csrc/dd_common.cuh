@@ -210,6 +210,11 @@ __device__ __forceinline__ f32x2_t fadd2_p(f32x2_t a, f32x2_t b) {
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
+// both halves of a packed pair from lane (self ^ mask)
+__device__ __forceinline__ f32x2_t shfl_xor_f32x2(f32x2_t v, int mask) {
+    const float2 f = unpack2(v);
+    return pack2(__shfl_xor_sync(0xffffffffu, f.x, mask), __shfl_xor_sync(0xffffffffu, f.y, mask));
+}
 // a + (lo, hi)
 __device__ __forceinline__ f32x2_t fadd2_s(f32x2_t a, float lo, float hi) {
     f32x2_t d;

@@ -226,7 +226,7 @@ constexpr int K2_COMPUTE = K2_WARPS * 32;
 constexpr int K2_THREADS = 2 * K2_COMPUTE;      // 8 DOT warps + 8 ACC warps
 // rows per batch: as many as fit 32 reduction lanes AND leave room for a 4-stage ring next to the transposition buffer
 __host__ __device__ constexpr int k2_rows(int K) { return K >= 1 ? 6 : 6; }
-constexpr int K2_TR = 34;                      // float2 per transposition row: 272 B keeps LDS.128 conflict-free
+constexpr int K2_TR = 18;                      // float2 per transposition row (16 half-warp partials + pad): 144 B keeps LDS.128 conflict-free
 constexpr int K2_MINK = 4;
 constexpr int K2_MAXK = 10;
 
@@ -243,6 +243,11 @@ constexpr int K2_MAXK = 10;
 // stage before arming the stage's `full` barrier, and a rows == 0 sentinel after the last batch.
 // The DOT warps run up to `stages` batches ahead, so a scheduler always has FMA-bound and latency-bound warps to
 // pick from (4 per scheduler instead of the 2 a 255-register thread allows).
+#ifdef DD_ALL_LANES_ARRIVE
+#define DD_CBAR_ARRIVALS_PER_WARP 32
+#else
+#define DD_CBAR_ARRIVALS_PER_WARP 1
+#endif
 constexpr int K2_CROSS = 4;  // cross buffers; the ring is capped at K2_CROSS stages so a buffer is never overwritten early
 
 template <int K, bool FULL>
@@ -272,7 +277,7 @@ kmeans_pair_kernel(const float* __restrict__ x, const int64_t* __restrict__ clas
 
     if (tid == 0) {
         for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 2 * K2_WARPS); }
-        for (int i = 0; i < K2_CROSS; ++i) mbar_init(&cbar[i], K2_WARPS);
+        for (int i = 0; i < K2_CROSS; ++i) mbar_init(&cbar[i], K2_WARPS * DD_CBAR_ARRIVALS_PER_WARP);
         mbar_fence_init();
     }
     if (tid < 16) cnt_s[tid] = 0;
@@ -345,8 +350,13 @@ kmeans_pair_kernel(const float* __restrict__ x, const int64_t* __restrict__ clas
                     }
 #pragma unroll
                 for (int p = 0; p < KP; ++p) {
-                    reinterpret_cast<f32x2_t*>(my_tr)[(r * KP + p) * K2_TR + lane] = dp0[p];
-                    reinterpret_cast<f32x2_t*>(my_tr)[((r + 1) * KP + p) * K2_TR + lane] = dp1[p];
+                    // lanes l and l^16 are added by shuffle first: half the transposition volume through shared memory
+                    // (the kernel is bound by its shared-memory wavefronts, not by issue slots)
+                    const f32x2_t s0 = fadd2_p(dp0[p], shfl_xor_f32x2(dp0[p], 16)), s1 = fadd2_p(dp1[p], shfl_xor_f32x2(dp1[p], 16));
+                    if (lane < 16) {
+                        reinterpret_cast<f32x2_t*>(my_tr)[(r * KP + p) * K2_TR + lane] = s0;
+                        reinterpret_cast<f32x2_t*>(my_tr)[((r + 1) * KP + p) * K2_TR + lane] = s1;
+                    }
                 }
             }
             __syncwarp();
@@ -361,7 +371,7 @@ kmeans_pair_kernel(const float* __restrict__ x, const int64_t* __restrict__ clas
                     c[2 * i] = pack2(u.x, u.y); c[2 * i + 1] = pack2(u.z, u.w);
                 }
 #pragma unroll
-                for (int i = 4; i < 16; ++i) {
+                for (int i = 4; i < 8; ++i) {
                     const float4 u = row[i];
                     c[(2 * i) & 7] = fadd2_s(c[(2 * i) & 7], u.x, u.y); c[(2 * i + 1) & 7] = fadd2_s(c[(2 * i + 1) & 7], u.z, u.w);
                 }
@@ -369,7 +379,11 @@ kmeans_pair_kernel(const float* __restrict__ x, const int64_t* __restrict__ clas
                 reinterpret_cast<f32x2_t*>(cross)[(buf * K2_WARPS + warp) * 32 + lane] = tot;
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&cbar[buf]);
+            // one elected lane arrives for the warp: __syncwarp orders the other lanes' stores before it, and the arrive
+            // releases them to the ACC warps' acquire (try_wait).  racecheck models happens-before per THREAD and flags the
+            // 31 lanes that never touch the barrier themselves; -DDD_ALL_LANES_ARRIVE (tools/gpu_sanitize.sh) makes every
+            // lane arrive, which the tool accepts -- same protocol, 32x the barrier traffic, so not the product setting.
+            if (DD_CBAR_ARRIVALS_PER_WARP == 32 || lane == 0) mbar_arrive(&cbar[buf]);
             advance();
         }
         return;

@@ -63,6 +63,14 @@ def main():
             per = -(-N // world); sl = slice(per * rank, min(per * (rank + 1), N))
             prototypes.build_prototypes(feats[sl].contiguous(), labels[sl].contiguous(), C, K, method, 3, coll=coll if method == "kmeans" else None)
         prototypes.build_prototypes(feats, labels, C, 3, "kmeans", 2, return_debug=True)     # inertia variant + partial_reduce
+        # the opt-in tensor-core variant of the pass (split-fp16 mma.sync), K = 4 and 10
+        perm, off = ops.sort_by_class(labels, C)
+        xs, _, _ = ops.rownorm_classsum(feats, perm, off)
+        for K in (4, 10):
+            buf = ops.KMeansBuffers(N, D, C, K, dev)
+            idx = off[:-1, None] + (torch.arange(K, device=dev)[None, :] * (off[1:] - off[:-1])[:, None]) // K
+            s_, c_ = ops.kmeans_seed(xs, idx.contiguous()); ops.kmeans_update(s_, c_, buf.centroid, buf.cnorm)
+            ops.kmeans_assign_accum(xs, off, buf, mma=True)
     torch.cuda.synchronize()
     if coll is not None:
         coll.close()

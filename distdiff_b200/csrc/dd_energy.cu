@@ -12,7 +12,7 @@
 //     where latency matters): prototypes come straight from L2.
 //   * energy_tile_kernel (large B): the prototype reads of the per-sample kernel are (K+3) rows of L2->SM traffic
 //     per sample against 2 rows of HBM traffic, i.e. L2-bound at ~0.25-0.36 of the HBM roofline.  The tile kernel
-//     removes them: samples are bucketed by class (a counting sort in two tiny kernels), persistent CTAs walk
+//     removes them: samples are bucketed by class (a counting sort in one small kernel), persistent CTAs walk
 //     contiguous runs of the class-sorted order, every thread OWNS 8 columns of D and keeps the class's K+1
 //     prototype slices in registers across the run, sample rows are gathered by the TMA engine (one
 //     cp.async.bulk per row through the permutation) into a shared-memory ring, and the per-sample sums
@@ -225,59 +225,87 @@ energy_kernel(const float* __restrict__ f, const int64_t* __restrict__ target, c
 // The order inside a bucket is arbitrary; every output is written at the sample's ORIGINAL index and the batch
 // mean is taken in index order, so results do not depend on it.
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(EN_THREADS)
-class_rank_kernel(const int64_t* __restrict__ target, int B, int C, int* __restrict__ counts /* [C+1], zero */,
-                  int* __restrict__ rank /* [B] */, int* __restrict__ off /* [C+2] */, unsigned int* __restrict__ ticket) {
-    __shared__ int wsum[EN_THREADS / 32];
-    __shared__ bool is_last;
-    const int b = blockIdx.x * EN_THREADS + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    const unsigned act = __ballot_sync(0xffffffffu, b < B);
-    if (b < B) {
-        const int64_t y = target[b];
-        const int c = (y >= 0 && y < C) ? (int)y : C;
-        const unsigned m = __match_any_sync(act, c);
-        const int leader = __ffs(m) - 1;
-        int base = 0;
-        if (lane == leader) base = atomicAdd(counts + c, __popc(m));
-        base = __shfl_sync(m, base, leader);
-        rank[b] = base + __popc(m & ((1u << lane) - 1u));
-    }
+constexpr int CS_SMEM_OFF = 4096;   // class offsets kept in shared memory by every CTA when C + 2 <= this
+
+// grid-wide barrier of a co-resident grid: `bar` counts arrivals (zeroed by the memset before the launch); `target`
+// = arrivals that complete this barrier
+__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int target) {
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) is_last = atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1;
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    // exclusive scan of counts[0..C] -> off[0..C+1]; thread t owns a contiguous chunk
-    const int n = C + 1;
-    const int per = (n + EN_THREADS - 1) / EN_THREADS;
-    const int lo = threadIdx.x * per, hi = min(lo + per, n);
-    int s = 0;
-    for (int i = lo; i < hi; ++i) s += __ldcg(counts + i);
-    int incl = s;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
+    if (threadIdx.x == 0) {
+        atomicAdd(bar, 1u);
+        unsigned int v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+            if (v < target) __nanosleep(32);
+        } while (v < target);
     }
-    if (lane == 31) wsum[threadIdx.x >> 5] = incl;
     __syncthreads();
-    int wbase = 0;
-    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) wbase += wsum[w];
-    int run = wbase + incl - s;
-    for (int i = lo; i < hi; ++i) { off[i] = run; run += __ldcg(counts + i); }
-    if (threadIdx.x == 0) off[n] = B;
 }
 
+// ONE launch: rank inside the class (warp-aggregated atomics) | grid barrier | exclusive scan of the class counts (every
+// CTA, in shared memory; CTA 0 also publishes off[] for the tile kernel) | scatter perm[off[c] + rank] = b.
+// grid <= 2 x #SMs CTAs of 256 threads (co-resident), grid-stride over the samples.
 __global__ void __launch_bounds__(EN_THREADS)
-class_scatter_kernel(const int64_t* __restrict__ target, int B, int C, const int* __restrict__ rank,
-                     const int* __restrict__ off, int* __restrict__ perm) {
-    const int b = blockIdx.x * EN_THREADS + threadIdx.x;
-    if (b >= B) return;
-    const int64_t y = target[b];
-    const int c = (y >= 0 && y < C) ? (int)y : C;
-    perm[off[c] + rank[b]] = b;
+class_sort_kernel(const int64_t* __restrict__ target, int B, int C, int* __restrict__ counts /* [C+1], zero */,
+                  int* __restrict__ rank /* [B] */, int* __restrict__ off /* [C+2] */, int* __restrict__ perm /* [B] */,
+                  unsigned int* __restrict__ bar /* zero */) {
+    __shared__ int soff[CS_SMEM_OFF];
+    __shared__ int wsum[EN_THREADS / 32];
+    const int lane = threadIdx.x & 31;
+    const int stride = gridDim.x * EN_THREADS;
+    pdl_launch_dependents();   // the tile kernel may be scheduled behind this grid (it waits for its completion before reading)
+    for (int b0 = blockIdx.x * EN_THREADS; b0 < B; b0 += stride) {
+        const int b = b0 + threadIdx.x;
+        const unsigned act = __ballot_sync(0xffffffffu, b < B);
+        if (b < B) {
+            const int64_t y = target[b];
+            const int c = (y >= 0 && y < C) ? (int)y : C;
+            const unsigned m = __match_any_sync(act, c);
+            const int leader = __ffs(m) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(counts + c, __popc(m));
+            base = __shfl_sync(m, base, leader);
+            rank[b] = base + __popc(m & ((1u << lane) - 1u));
+        }
+    }
+    grid_barrier(bar, gridDim.x);
+    // exclusive scan of counts[0..C] -> offsets; thread t owns a contiguous chunk
+    const int n = C + 1;
+    const bool in_smem = n + 1 <= CS_SMEM_OFF;
+    if (in_smem || blockIdx.x == 0) {
+        const int per = (n + EN_THREADS - 1) / EN_THREADS;
+        const int lo = threadIdx.x * per, hi = min(lo + per, n);
+        int sacc = 0;
+        for (int i = lo; i < hi; ++i) sacc += __ldcg(counts + i);
+        int incl = sacc;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) wsum[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        int wbase = 0;
+        for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) wbase += wsum[w];
+        int run = wbase + incl - sacc;
+        for (int i = lo; i < hi; ++i) {
+            if (in_smem) soff[i] = run;
+            if (blockIdx.x == 0) off[i] = run;
+            run += __ldcg(counts + i);
+        }
+        if (threadIdx.x == 0 && blockIdx.x == 0) off[n] = B;
+        __syncthreads();
+    }
+    if (!in_smem) grid_barrier(bar, 2 * gridDim.x);   // huge class counts: the offsets come from CTA 0 through global memory
+    for (int b0 = blockIdx.x * EN_THREADS; b0 < B; b0 += stride) {
+        const int b = b0 + threadIdx.x;
+        if (b < B) {
+            const int64_t y = target[b];
+            const int c = (y >= 0 && y < C) ? (int)y : C;
+            perm[(in_smem ? soff[c] : __ldcg(off + c)) + rank[b]] = b;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -412,6 +440,7 @@ energy_tile_kernel(const float* __restrict__ f, const int* __restrict__ perm, co
         mbar_fence_init();
     }
     __syncthreads();
+    pdl_wait();   // perm / off come from the sort kernel launched right before (programmatic dependent launch)
 
     // walk over the class-sorted positions [r0, r1) in batches of <= R rows of one class (32-bit cursors)
     auto take = [&](int& row, int& c, int& end, int& b_row, int& b_n, int& b_c) {
@@ -757,11 +786,11 @@ static int launch_energy_tile(const float* f, const int64_t* target, const float
     int* off = (int*)(ws + w.off_off);
     int* rank = (int*)(ws + w.rank_off);
     int* perm = (int*)(ws + w.perm_off);
-    DD_CUDA_OK(cudaMemsetAsync(counts, 0, ((size_t)C + 1) * sizeof(int), st));
-    const unsigned pg = (unsigned)((B + EN_THREADS - 1) / EN_THREADS);
-    class_rank_kernel<<<pg, EN_THREADS, 0, st>>>(target, B, C, counts, rank, off, ticket2);
-    DD_LAUNCH_OK();
-    class_scatter_kernel<<<pg, EN_THREADS, 0, st>>>(target, B, C, rank, off, perm);
+    // ticket2 (the sort kernel's grid-barrier counter) sits right before counts: one memset clears both
+    DD_CUDA_OK(cudaMemsetAsync(ticket2, 0, (size_t)(w.counts_off - w.ticket2_off) + ((size_t)C + 1) * sizeof(int), st));
+    unsigned pg = (unsigned)((B + EN_THREADS - 1) / EN_THREADS);
+    if (pg > 2u * (unsigned)sm_count()) pg = 2u * (unsigned)sm_count();   // co-resident: the kernel has a grid barrier
+    class_sort_kernel<<<pg, EN_THREADS, 0, st>>>(target, B, C, counts, rank, off, perm, ticket2);
     DD_LAUNCH_OK();
     using Cfg = TileCfg<KT>;
     const size_t ring_bytes = (Cfg::CTAS_PER_SM == 2 ? 100 * 1024 : 208 * 1024) - Cfg::SMEM_FIXED;
@@ -774,15 +803,22 @@ static int launch_energy_tile(const float* f, const int64_t* target, const float
     DD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int G = Cfg::CTAS_PER_SM * sm_count();
     if (G > (B + ET_R - 1) / ET_R) G = (B + ET_R - 1) / ET_R;
-    kern<<<G, EN_THREADS, smem, st>>>(f, perm, off, g, l, B, D, C, K, gs, ls, normalize_f, score, per_sample, kstar, grad_f,
-                                      ticket, stages);
-    DD_LAUNCH_OK();
+    // programmatic dependent launch behind the sort kernel: barrier init and scheduling overlap its tail
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(G); cfg.blockDim = dim3(EN_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    DD_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, f, (const int*)perm, (const int*)off, g, l, B, D, C, K, gs, ls, normalize_f, score, per_sample,
+                                  kstar, grad_f, ticket, stages));
     return 0;
 }
 
-// smallest B the class-tiled kernel takes in auto mode: below it the three extra tiny launches of the class
-// bucketing cost more than the L2 traffic they save
-static int tile_min_b() { return 16 * sm_count(); }
+// smallest B the class-tiled kernel takes in auto mode: below it the class bucketing (a memset + one small kernel) costs
+// more than the L2 traffic it saves -- measured break-even ~1k samples for K >= 5 (more prototype rows per sample to
+// save), ~2k for fewer clusters
+static int tile_min_b(int K) { return (K >= 5 ? 7 : 16) * sm_count(); }
 
 }  // namespace dd
 
@@ -810,7 +846,7 @@ extern "C" int dd_energy_fwd_bwd(const float* f, const int64_t* target, const fl
     const bool tile_ok = D <= dd::PK_MAX_D && ws_bytes >= dd::energy_ws(B, C).total;
     DD_REQUIRE(mode != 2 || tile_ok, DD_EUNSUPPORTED, "dd_energy_fwd_bwd: class-tiled kernel needs D <= %d and a %zu-byte workspace",
                dd::PK_MAX_D, dd::energy_ws(B, C).total);
-    if (mode == 2 || (mode == 0 && tile_ok && B >= dd::tile_min_b())) {
+    if (mode == 2 || (mode == 0 && tile_ok && B >= dd::tile_min_b(K))) {
 #define ARGS f, target, g, l, B, D, C, K, gs, ls, normalize_f, score, per_sample, kstar, grad_f, (unsigned char*)ws, st
         if (K <= 3) return dd::launch_energy_tile<3>(ARGS);
         if (K <= 4) return dd::launch_energy_tile<4>(ARGS);

@@ -336,7 +336,7 @@ def energy_fwd_bwd(f: torch.Tensor, targets, g: Optional[torch.Tensor], l: Optio
     ws = _energy_workspace(f.device, B, Cn)
     # algorithmic bytes (compulsory HBM traffic): f read + grad written + the prototype tables once
     tiled = mode == "tile" or (mode == "auto" and D <= 2048 and
-                               B >= 16 * torch.cuda.get_device_properties(f.device).multi_processor_count)
+                               B >= (7 if K >= 5 else 16) * torch.cuda.get_device_properties(f.device).multi_processor_count)
     _call("dd_energy_fwd_bwd", 2 * B * D * 4 + (int(g is not None) + (K if l is not None else 0)) * Cn * D * 4, 3 if tiled else 1,
           _ptr(f), _ptr(y), _ptr(g), _ptr(l), B, D, Cn, K, float(gs), float(ls),
                                        int(bool(normalize_f)), _ptr(score), _ptr(per), _ptr(kstar), _ptr(grad),

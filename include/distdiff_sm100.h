@@ -113,7 +113,7 @@ int dd_image_to_uint8(const void* img, int64_t B, int C, int H, int W, int dtype
  * kstar [B] i32, grad_f [B,D] f32.
  * ws: caller-owned device workspace, 16-byte aligned, ZERO before first use (the kernels leave it reusable); one
  * workspace per stream.  >= 16 bytes always works (one CTA per sample); with dd_energy_workspace_bytes(B, C)
- * bytes a large batch (B >= 16 x #SMs, D <= 2048) is bucketed by class and runs the class-tiled kernel (prototype
+ * bytes a large batch (B >= 16 x #SMs, or 7 x #SMs for K >= 5; D <= 2048) is bucketed by class and runs the class-tiled kernel (prototype
  * slices in registers, sample rows gathered by TMA) -- same results, HBM-bound instead of L2-bound.
  * mode: 0 = choose by size, 1 = one CTA per sample, 2 = class-tiled (needs the full workspace). */
 size_t dd_energy_workspace_bytes(int B, int C);

@@ -58,6 +58,7 @@ def parse():
     p.add_argument("--batch", type=int, default=8, help="images per step and GPU (train_batch_size)")
     p.add_argument("--dtype", default=None, choices=["fp16", "bf16", "fp32"], help="UNet/VAE/latent storage type (reference: fp16)")
     p.add_argument("--no-cuda-graph", action="store_true")
+    p.add_argument("--grad-ckpt", action="store_true", help="UNet gradient checkpointing in the guided step (generate_data.py:1049-1050): memory vs time")
     p.add_argument("--no-channels-last", action="store_true", help="keep UNet/VAE/guide in NCHW (PyTorch-side layout choice)")
     p.add_argument("--no-kernels", action="store_true", help="skip the batched kernel micro-benchmarks")
     p.add_argument("--no-cpu-baseline", action="store_true")
@@ -279,6 +280,8 @@ def run_ours(opt):
     C = a.num_classes
     wd = {"fp16": torch.float16, "bf16": torch.bfloat16, "fp32": torch.float32}[opt.dtype]
     unet, vae, guide = build_models(opt.tiny, num_classes=C)
+    if opt.grad_ckpt:
+        unet.enable_gradient_checkpointing()
     unet.to(dev, wd); vae.to(dev, wd); guide.to(dev)
     if not opt.no_channels_last:   # PyTorch-side: NHWC weights let cuDNN skip its per-conv nchw<->nhwc transposes (14 % of a step)
         for m in (unet, vae, guide):
@@ -516,7 +519,8 @@ def run_ours(opt):
                         "includes": "fresh pinned host batch per step, H2D, K9 bytes D2H, PNG encode + atomic publish (drained inside the region), score read"},
                 "gpu_launches": launches, "clocks": clocks, "gpu_busy_timed_regions": gpu_busy, "roofline": roofline,
                 "kernels_in_step": kernels_in_step, "prototype_construction_s": round(t_proto, 4),
-                "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1), "tiny": bool(opt.tiny)}
+                "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1), "gradient_checkpointing": bool(opt.grad_ckpt),
+                "tiny": bool(opt.tiny)}
         if dist_parity is not None:
             line["dist_parity"] = dist_parity
         if proto_sweep is not None:

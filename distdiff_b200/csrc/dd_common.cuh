@@ -47,8 +47,8 @@ int kmeans_pass(const float* x_sorted, const int64_t* class_off, int64_t N, int 
 // K3 on the tensor cores (dd_kmeans_mma.cu)
 bool kmeans_mma_supported(int K, int D);
 int launch_kmeans_mma(int K, const float* x, const int64_t* class_off, int64_t N, int D, int C, const float* centroid,
-                      const float* cnorm, int32_t* assign, double* ws_sum, int64_t* ws_cnt, int G, bool pdl, cudaStream_t st);
-void kmeans_ws_slots(void* ws, int D, int C, int K, const double** ws_sum, const int64_t** ws_cnt, int* G);
+                      const float* cnorm, int32_t* assign, float* ws_sum, int64_t* ws_cnt, int G, bool pdl, cudaStream_t st);
+void kmeans_ws_slots(void* ws, int D, int C, int K, const float** ws_sum, const int64_t** ws_cnt, int* G);
 // centroid update; with `ws` it first adds the pass's partial slots (fixed order).  pdl: programmatic dependent launch
 int kmeans_update_launch(double* sum, int64_t* cnt, int C, int K, int D, float* centroid, float* cnorm, bool pdl, const void* ws,
                          const int64_t* class_off, int64_t N, cudaStream_t st);

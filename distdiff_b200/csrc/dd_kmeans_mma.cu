@@ -84,7 +84,7 @@ template <int K, bool FULL>
 __global__ void __launch_bounds__(KM_THREADS, 1)
 kmeans_mma_kernel(const float* __restrict__ x, const int64_t* __restrict__ class_off, int64_t N, int D_, int C,
                   const float* __restrict__ centroid, const float* __restrict__ cnorm, int32_t* __restrict__ assign,
-                  double* __restrict__ ws_sum, int64_t* __restrict__ ws_cnt) {
+                  float* __restrict__ ws_sum, int64_t* __restrict__ ws_cnt) {
     static_assert(K >= 1 && K <= 16, "at most one m16 tile of clusters");
     constexpr int R = KM_R;
     const int D = FULL ? PK_MAX_D : D_;
@@ -137,7 +137,7 @@ kmeans_mma_kernel(const float* __restrict__ x, const int64_t* __restrict__ class
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const float2 a0 = unpack2(acc[k][0]), a1 = unpack2(acc[k][1]);
-            if (own) store_f64x4(ws_sum + (slot * K + k) * D + tid * 4, (double)a0.x, (double)a0.y, (double)a1.x, (double)a1.y);
+            if (own) *reinterpret_cast<float4*>(ws_sum + (slot * K + k) * D + tid * 4) = make_float4(a0.x, a0.y, a1.x, a1.y);
             acc[k][0] = 0ull; acc[k][1] = 0ull;
         }
         __syncthreads();   // every warp's count updates of the class are in cnt_s
@@ -246,7 +246,7 @@ kmeans_mma_kernel(const float* __restrict__ x, const int64_t* __restrict__ class
 
 template <int K>
 int launch_kmeans_mma_k(const float* x, const int64_t* class_off, int64_t N, int D, int C, const float* centroid, const float* cnorm,
-                        int32_t* assign, double* ws_sum, int64_t* ws_cnt, int G, bool pdl, cudaStream_t st) {
+                        int32_t* assign, float* ws_sum, int64_t* ws_cnt, int G, bool pdl, cudaStream_t st) {
     const size_t smem = (size_t)KM_STAGES * KM_R * (D + KM_PAD) * sizeof(float) + sizeof(KmSmem);
     DD_REQUIRE(smem <= 227 * 1024, DD_EUNSUPPORTED, "kmeans (mma): D=%d too large for the shared-memory ring", D);
     auto kern = (D == PK_MAX_D) ? kmeans_mma_kernel<K, true> : kmeans_mma_kernel<K, false>;
@@ -265,7 +265,7 @@ int launch_kmeans_mma_k(const float* x, const int64_t* class_off, int64_t N, int
 bool kmeans_mma_supported(int K, int D) { return K >= 4 && K <= 10 && D % 256 == 0 && D >= 256 && D <= PK_MAX_D; }
 
 int launch_kmeans_mma(int K, const float* x, const int64_t* class_off, int64_t N, int D, int C, const float* centroid,
-                      const float* cnorm, int32_t* assign, double* ws_sum, int64_t* ws_cnt, int G, bool pdl, cudaStream_t st) {
+                      const float* cnorm, int32_t* assign, float* ws_sum, int64_t* ws_cnt, int G, bool pdl, cudaStream_t st) {
 #define DD_KMM(KK) case KK: return launch_kmeans_mma_k<KK>(x, class_off, N, D, C, centroid, cnorm, assign, ws_sum, ws_cnt, G, pdl, st);
     switch (K) { DD_KMM(4) DD_KMM(5) DD_KMM(6) DD_KMM(7) DD_KMM(8) DD_KMM(9) DD_KMM(10) }
 #undef DD_KMM

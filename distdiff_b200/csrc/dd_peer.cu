@@ -27,7 +27,7 @@ namespace dd {
 
 constexpr int PEER_MAX = 16;
 constexpr int PEER_THREADS = 256;
-constexpr int CPT = 8;              // columns per thread and pass of the exchange kernel
+constexpr int CPT = 4;              // columns per thread and pass of the exchange kernel (x 8 peers of loads in flight)
 constexpr size_t PEER_HDR = 1024;   // flag rows A [64], B [64], status, ticket (uint32)
 
 constexpr size_t PEER_STAMP_OFF = 544;   // 8 x u64 %globaltimer stamps of the last exchange (phase boundaries, dd_peer_timing)
@@ -76,7 +76,7 @@ __device__ __forceinline__ bool wait_all(const uint32_t* flags, int world, uint3
 __global__ void __launch_bounds__(PEER_THREADS)
 kmeans_exchange_kernel(unsigned char* me, int rank, int world, uint32_t epoch, size_t off_sum, size_t off_cnt, size_t off_cen,
                        size_t off_cn, size_t off_gcnt, int R, int D, unsigned long long timeout_ns,
-                       const double* __restrict__ ws_sum /* null: the local sums are final */, const int64_t* __restrict__ ws_cnt,
+                       const float* __restrict__ ws_sum /* null: the local sums are final */, const int64_t* __restrict__ ws_cnt,
                        const int64_t* __restrict__ class_off, int64_t N, int K, int G) {
     __shared__ double sh[PEER_THREADS / 32];
     __shared__ unsigned char* peer[PEER_MAX];
@@ -110,12 +110,14 @@ kmeans_exchange_kernel(unsigned char* me, int rank, int world, uint32_t epoch, s
             }
             if (threadIdx.x == 0) my_cnt[r] = n;
         }
-        __threadfence_system();
+        // one system-scope fence per CTA, by the thread that takes the ticket: the CTA barrier orders the other threads'
+        // stores before it (fences are cumulative) -- a fence in every thread costs 256 MEMBAR.SYS per CTA
         __syncthreads();
         if (threadIdx.x == 0) {
+            __threadfence_system();
             const unsigned t = atomicAdd(ticket0, 1u);
             last = (t == gridDim.x - 1);
-            if (last) *ticket0 = 0u;
+            if (last) { *ticket0 = 0u; __threadfence_system(); }
         }
         __syncthreads();
         signal = last;
@@ -142,18 +144,26 @@ kmeans_exchange_kernel(unsigned char* me, int rank, int world, uint32_t epoch, s
             double s[CPT];
 #pragma unroll
             for (int j = 0; j < CPT; ++j) s[j] = 0.0;
-            {   // (loaded even when the row turns out empty: the count loads above then overlap these instead of gating them)
-#pragma unroll 4
-                for (int p = 0; p < world; ++p) {
+            // all peers' loads of a pass are issued before the ordered adds (8 peers at a time): one NVLink round trip
+            // serves the row (also when it turns out empty: the count loads above overlap these instead of gating them)
+            for (int p0 = 0; p0 < world; p0 += 8) {
+                double v[8][CPT];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int p = p0 + i < world ? p0 + i : world - 1;
                     const double* src = reinterpret_cast<const double*>(peer[p] + off_sum) + (size_t)r * D;
-                    double v[CPT];
 #pragma unroll
                     for (int j = 0; j < CPT; ++j) {
                         const int col = c0 + threadIdx.x + j * PEER_THREADS;
-                        v[j] = col < D ? __ldcg(src + col) : 0.0;
+                        v[i][j] = (p0 + i < world && col < D) ? __ldcg(src + col) : 0.0;
                     }
+                }
 #pragma unroll
-                    for (int j = 0; j < CPT; ++j) s[j] += v[j];   // rank order
+                for (int i = 0; i < 8; ++i) {
+                    if (p0 + i < world) {
+#pragma unroll
+                        for (int j = 0; j < CPT; ++j) s[j] += v[i][j];   // rank order
+                    }
                 }
             }
             float m[CPT];
@@ -186,12 +196,12 @@ kmeans_exchange_kernel(unsigned char* me, int rank, int world, uint32_t epoch, s
     }
 
     // B: everything this CTA stored is visible system-wide before the flag; the last CTA of the grid signals
-    __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
+        __threadfence_system();
         const unsigned t = atomicAdd(ticket, 1u);
         last = (t == gridDim.x - 1);
-        if (last) *ticket = 0u;   // ready for the next launch (stream-ordered)
+        if (last) { *ticket = 0u; __threadfence_system(); }   // ready for the next launch (stream-ordered)
     }
     __syncthreads();
     if (!last) return;
@@ -205,11 +215,17 @@ kmeans_exchange_kernel(unsigned char* me, int rank, int world, uint32_t epoch, s
 }
 
 static int exchange_launch(PeerCtx* c, size_t off_sum, size_t off_cnt, size_t off_cen, size_t off_cn, size_t off_gcnt, int R, int D,
-                           bool pdl, const double* ws_sum, const int64_t* ws_cnt, const int64_t* class_off, int64_t N, int K, int G,
+                           bool pdl, const float* ws_sum, const int64_t* ws_cnt, const int64_t* class_off, int64_t N, int K, int G,
                            cudaStream_t st) {
     const int rows = (int)((int64_t)R * (c->rank + 1) / c->world - (int64_t)R * c->rank / c->world);
     int grid = ws_sum ? R : (rows < 1 ? 1 : rows);      // with the slot reduction every row of the table is local work
-    if (grid > 2 * c->sm_count) grid = 2 * c->sm_count;  // all CTAs spin on flags: they must be co-resident
+    static int per_sm = 0;                               // all CTAs spin on flags and tickets: they must be co-resident
+    if (per_sm == 0) {
+        DD_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kmeans_exchange_kernel, PEER_THREADS, 0));
+        if (per_sm < 1) per_sm = 1;
+        if (per_sm > 2) per_sm = 2;
+    }
+    if (grid > per_sm * c->sm_count) grid = per_sm * c->sm_count;
     c->epoch += 1;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(PEER_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = st;
@@ -313,7 +329,7 @@ int dd_kmeans_lloyd(const float* x_sorted, const int64_t* class_off, int64_t N, 
     // the next pass's prologue (ring prefill from HBM) runs under the exchange's tail.  The NCCL path keeps the
     // separate reduce launch (the all-reduce needs the local sums in place) and serves as the cross-check.
     cudaStream_t st = (cudaStream_t)stream;
-    const double* ws_sum = nullptr;
+    const float* ws_sum = nullptr;
     const int64_t* ws_cnt = nullptr;
     int G = 1;
     const bool slots = !nccl_comm && N > 0 && D <= dd::PK_MAX_D;

@@ -33,7 +33,7 @@ template <int K, int R, bool INERTIA>
 __global__ void __launch_bounds__(PK_THREADS, 1)
 kmeans_stream_kernel(const float* __restrict__ x, const int64_t* __restrict__ class_off, int64_t N, int D, int C,
                      const float* __restrict__ centroid, const float* __restrict__ cnorm, int32_t* __restrict__ assign,
-                     double* __restrict__ ws_sum, int64_t* __restrict__ ws_cnt, double* __restrict__ ws_inertia,
+                     float* __restrict__ ws_sum, int64_t* __restrict__ ws_cnt, double* __restrict__ ws_inertia,
                      int stages) {
     constexpr int KV = K + (INERTIA ? 1 : 0);  // reduced values per row: K dots (+ ||x||^2)
     constexpr int V = R * KV;
@@ -89,8 +89,8 @@ kmeans_stream_kernel(const float* __restrict__ x, const int64_t* __restrict__ cl
 #pragma unroll
             for (int ch = 0; ch < PK_CH; ++ch)
                 if (own[ch])
-                    store_f64x4(ws_sum + (slot * K + k) * D + chunk[ch] * 4, (double)acc[k][ch][0], (double)acc[k][ch][1],
-                                (double)acc[k][ch][2], (double)acc[k][ch][3]);
+                    *reinterpret_cast<float4*>(ws_sum + (slot * K + k) * D + chunk[ch] * 4) =
+                        make_float4(acc[k][ch][0], acc[k][ch][1], acc[k][ch][2], acc[k][ch][3]);
             if (tid == 0) ws_cnt[slot * K + k] = cnt[k];
         }
     };
@@ -254,7 +254,7 @@ template <int K, bool FULL>
 __global__ void __launch_bounds__(K2_THREADS, 1)
 kmeans_pair_kernel(const float* __restrict__ x, const int64_t* __restrict__ class_off, int64_t N, int D, int C,
                    const float* __restrict__ centroid, const float* __restrict__ cnorm, int32_t* __restrict__ assign,
-                   double* __restrict__ ws_sum, int64_t* __restrict__ ws_cnt, int stages) {
+                   float* __restrict__ ws_sum, int64_t* __restrict__ ws_cnt, int stages) {
     constexpr int KP = (K + 1) / 2;   // cluster pairs
     constexpr int R = k2_rows(K);
     constexpr int SLOTS = R * KP;     // packed partials per batch (<= 30): one per lane in the reduction
@@ -429,10 +429,10 @@ kmeans_pair_kernel(const float* __restrict__ x, const int64_t* __restrict__ clas
         const int64_t slot = (int64_t)g + c;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            double* dst = ws_sum + (slot * K + k) * D;
+            float* dst = ws_sum + (slot * K + k) * D;
             const float2 a0 = unpack2(acc[k][0]), a1 = unpack2(acc[k][1]), a2 = unpack2(acc[k][2]), a3 = unpack2(acc[k][3]);
-            if (own0) store_f64x4(dst + chunk0 * 4, (double)a0.x, (double)a0.y, (double)a1.x, (double)a1.y);
-            if (own1) store_f64x4(dst + chunk1 * 4, (double)a2.x, (double)a2.y, (double)a3.x, (double)a3.y);
+            if (own0) *reinterpret_cast<float4*>(dst + chunk0 * 4) = make_float4(a0.x, a0.y, a1.x, a1.y);
+            if (own1) *reinterpret_cast<float4*>(dst + chunk1 * 4) = make_float4(a2.x, a2.y, a3.x, a3.y);
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[k][j] = 0ull;
         }
@@ -645,8 +645,9 @@ rownorm_stream_kernel(const float* __restrict__ feat, const int64_t* __restrict_
 // ---------------------------------------------------------------------------------------------------
 // fixed-order reduction of the per-(CTA, class) partial slots  ->  sum [C,K,D] f64, cnt [C,K] i64
 // ---------------------------------------------------------------------------------------------------
+template <typename SlotT>
 __global__ void __launch_bounds__(PK_THREADS)
-partial_reduce_kernel(const double* __restrict__ ws_sum, const int64_t* __restrict__ ws_cnt,
+partial_reduce_kernel(const SlotT* __restrict__ ws_sum, const int64_t* __restrict__ ws_cnt,
                       const double* __restrict__ ws_inertia, const int64_t* __restrict__ class_off, int64_t N, int D, int C,
                       int K, int G, double* __restrict__ sum, int64_t* __restrict__ cnt, double* __restrict__ inertia) {
     const int c = blockIdx.x / K, k = blockIdx.x % K;
@@ -715,7 +716,7 @@ kmeans_seed_kernel(const float* __restrict__ x, const int64_t* __restrict__ row_
 // row's fp64 sum and count are formed from the slots, written to sum / cnt, and used.
 __global__ void __launch_bounds__(PK_THREADS)
 kmeans_update_kernel(double* __restrict__ sum, int64_t* __restrict__ cnt, int D, float* __restrict__ centroid,
-                     float* __restrict__ cnorm, const double* __restrict__ ws_sum, const int64_t* __restrict__ ws_cnt,
+                     float* __restrict__ cnorm, const float* __restrict__ ws_sum, const int64_t* __restrict__ ws_cnt,
                      const int64_t* __restrict__ class_off, int64_t N, int K, int G) {
     __shared__ double sh[PK_WARPS];
     __shared__ int64_t s_n;
@@ -799,7 +800,7 @@ static size_t smem_bytes(int stages, int R, int D) {
 
 template <int K, int R, bool INERTIA>
 static int launch_kmeans(const float* x, const int64_t* class_off, int64_t N, int D, int C, const float* centroid,
-                         const float* cnorm, int32_t* assign, double* ws_sum, int64_t* ws_cnt, double* ws_inertia, int G,
+                         const float* cnorm, int32_t* assign, float* ws_sum, int64_t* ws_cnt, double* ws_inertia, int G,
                          bool pdl, cudaStream_t st) {
     const int stages = pick_stages(R, D);
     DD_REQUIRE(stages >= 2, DD_EUNSUPPORTED, "kmeans: D=%d too large for the shared-memory ring", D);
@@ -820,7 +821,7 @@ static size_t k2_smem_bytes(int stages, int D, int K) {
 
 template <int K>
 static int launch_kmeans_pair(const float* x, const int64_t* class_off, int64_t N, int D, int C, const float* centroid,
-                              const float* cnorm, int32_t* assign, double* ws_sum, int64_t* ws_cnt, int G, bool pdl,
+                              const float* cnorm, int32_t* assign, float* ws_sum, int64_t* ws_cnt, int G, bool pdl,
                               cudaStream_t st) {
     const size_t limit = 227 * 1024;
     int stages = K2_CROSS;
@@ -851,7 +852,7 @@ int kmeans_pass(const float* x_sorted, const int64_t* class_off, int64_t N, int 
     const int G = sm_count();
     const WsLayout w = ws_layout(D, C, K, G);
     DD_REQUIRE(ws_bytes >= w.total, DD_EWORKSPACE, "dd_kmeans_assign_accum: workspace %zu < %zu bytes", ws_bytes, w.total);
-    double* ws_sum = (double*)((char*)ws + w.sum_off);
+    float* ws_sum = (float*)((char*)ws + w.sum_off);   // K3 slots are fp32 (the layout reserves fp64-sized rows: K1 shares it)
     int64_t* ws_cnt = (int64_t*)((char*)ws + w.cnt_off);
     double* ws_in = (double*)((char*)ws + w.inertia_off);
     const bool pdl = (flags & KP_PDL) != 0;
@@ -888,24 +889,24 @@ int kmeans_pass(const float* x_sorted, const int64_t* class_off, int64_t N, int 
         DD_CUDA_OK(cudaMemsetAsync(ws_in, 0, (size_t)G * sizeof(double), st));
     }
     if (!(flags & KP_NO_REDUCE)) {
-        partial_reduce_kernel<<<C * K, PK_THREADS, 0, st>>>(ws_sum, ws_cnt, ws_in, class_off, N > 0 ? N : 1, D, C, K, G, sum, cnt,
-                                                           inertia);
+        partial_reduce_kernel<float><<<C * K, PK_THREADS, 0, st>>>(ws_sum, ws_cnt, ws_in, class_off, N > 0 ? N : 1, D, C, K, G, sum, cnt,
+                                                                  inertia);
         DD_LAUNCH_OK();
     }
     return 0;
 }
 
 // slot pointers of a pass's workspace, for the consumers that reduce the slots themselves
-void kmeans_ws_slots(void* ws, int D, int C, int K, const double** ws_sum, const int64_t** ws_cnt, int* G) {
+void kmeans_ws_slots(void* ws, int D, int C, int K, const float** ws_sum, const int64_t** ws_cnt, int* G) {
     *G = sm_count();
     const WsLayout w = ws_layout(D, C, K, *G);
-    *ws_sum = (const double*)((char*)ws + w.sum_off);
+    *ws_sum = (const float*)((char*)ws + w.sum_off);
     *ws_cnt = (const int64_t*)((char*)ws + w.cnt_off);
 }
 
 int kmeans_update_launch(double* sum, int64_t* cnt, int C, int K, int D, float* centroid, float* cnorm, bool pdl,
                          const void* ws /* null: sum / cnt are final */, const int64_t* class_off, int64_t N, cudaStream_t st) {
-    const double* ws_sum = nullptr;
+    const float* ws_sum = nullptr;
     const int64_t* ws_cnt = nullptr;
     int G = 0;
     if (ws) kmeans_ws_slots(const_cast<void*>(ws), D, C, K, &ws_sum, &ws_cnt, &G);
@@ -949,7 +950,7 @@ int dd_rownorm_classsum(const float* feat, const int64_t* perm, const int64_t* c
         kern<<<G, dd::PK_THREADS, smem, st>>>(feat, perm, class_off, N, D, C, feat_sorted, ws_sum, ws_cnt, stages);
         DD_LAUNCH_OK();
     }
-    dd::partial_reduce_kernel<<<C, dd::PK_THREADS, 0, st>>>(ws_sum, ws_cnt, nullptr, class_off, N > 0 ? N : 1, D, C, 1, G,
+    dd::partial_reduce_kernel<double><<<C, dd::PK_THREADS, 0, st>>>(ws_sum, ws_cnt, nullptr, class_off, N > 0 ? N : 1, D, C, 1, G,
                                                            class_sum, class_cnt, nullptr);
     DD_LAUNCH_OK();
     return 0;

@@ -107,7 +107,10 @@ __device__ __forceinline__ bool cta_hits(int g, int G, int64_t N, int64_t lo, in
     return (a > lo ? a : lo) < (b < hi ? b : hi);
 }
 
-__device__ __forceinline__ void slot_row_sum(const double* __restrict__ ws_sum, const int64_t* __restrict__ ws_cnt,
+// SlotT: double for K1's class sums (fp64 accumulators), float for the K3 passes (their per-CTA partials are fp32
+// accumulations: storing them as fp32 halves the slot traffic, the values -- and therefore the fp64 sums -- are the same)
+template <typename SlotT>
+__device__ __forceinline__ void slot_row_sum(const SlotT* __restrict__ ws_sum, const int64_t* __restrict__ ws_cnt,
                                              const int64_t* __restrict__ class_off, int64_t N, int D, int c, int k, int K, int G,
                                              double (&acc)[SLOT_NC], int64_t& n) {
     const int64_t lo = class_off[c], hi = class_off[c + 1];
@@ -120,16 +123,30 @@ __device__ __forceinline__ void slot_row_sum(const double* __restrict__ ws_sum, 
 #pragma unroll
     for (int j = 0; j < SLOT_NC; ++j) acc[j] = 0.0;
     n = 0;
-    // CTA loop outside, columns inside: the SLOT_NC column loads of a slot are independent
-    for (int g = g_lo; g <= g_hi; ++g) {
-        if (!dense && !cta_hits(g, G, N, lo, hi)) continue;
-        const double* src = ws_sum + (((int64_t)g + c) * K + k) * D;
+    // up to 4 slots (x SLOT_NC columns) are loaded before any is added: one memory round trip serves the typical row
+    // (a class spans 2-3 CTAs); the adds stay in ascending g
+    for (int g0 = g_lo; g0 <= g_hi; g0 += 4) {
+        double v[4][SLOT_NC];
+        bool on[4];
 #pragma unroll
-        for (int j = 0; j < SLOT_NC; ++j) {
-            const int col = threadIdx.x + j * PK_THREADS;
-            if (col < D) acc[j] += __ldcg(src + col);
+        for (int i = 0; i < 4; ++i) {
+            const int g = g0 + i;
+            on[i] = g <= g_hi && (dense || cta_hits(g, G, N, lo, hi));
+            const SlotT* src = ws_sum + (((int64_t)g + c) * K + k) * D;
+#pragma unroll
+            for (int j = 0; j < SLOT_NC; ++j) {
+                const int col = threadIdx.x + j * PK_THREADS;
+                v[i][j] = (on[i] && col < D) ? (double)__ldcg(src + col) : 0.0;
+            }
         }
-        if (threadIdx.x == 0) n += __ldcg(ws_cnt + ((int64_t)g + c) * K + k);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (on[i]) {
+#pragma unroll
+                for (int j = 0; j < SLOT_NC; ++j) acc[j] += v[i][j];
+                if (threadIdx.x == 0) n += __ldcg(ws_cnt + ((int64_t)(g0 + i) + c) * K + k);
+            }
+        }
     }
 }
 

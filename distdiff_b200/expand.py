@@ -94,6 +94,8 @@ class _GraphedGuidance:
             for _ in range(2):   # warm-up outside capture (cuDNN autotune for the backward convs, workspaces)
                 run()
         torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()   # the warm-up's ~9 GB per image sit cached in the default pool; the capture allocates from its own
         with torch.cuda.graph(self.graph, pool=expander._graph_pool):
             self.out_lat, self.out_score = run()
 

@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libdistdiff_sm100.so")
+# DD_LIB_PATH: development only -- load an experimental build of the same library (tools/build_variant.sh)
+LIB_PATH = os.environ.get("DD_LIB_PATH") or os.path.join(HERE, "libdistdiff_sm100.so")
 
 DD_F32, DD_F16, DD_BF16 = 0, 1, 2
 ABI_VERSION = 1

@@ -15,8 +15,9 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-BUILD = os.path.join(HERE, "_build")
-LIB = os.path.join(HERE, "libdistdiff_sm100.so")
+# DD_LIB_OUT / DD_BUILD_DIR: development only -- an experimental variant next to the product build (tools/build_variant.sh)
+BUILD = os.environ.get("DD_BUILD_DIR") or os.path.join(HERE, "_build")
+LIB = os.environ.get("DD_LIB_OUT") or os.path.join(HERE, "libdistdiff_sm100.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr"]

@@ -49,6 +49,37 @@ __device__ __forceinline__ void group_sum(float (&v)[NV], float* red /* [NV][8] 
     }
 }
 
+// deterministic batch mean, run by the last CTA to arrive: thread t sums samples t, t+T, ... in index order (two samples per
+// 16-byte load, 4 loads in flight), then a fixed-shape tree over the T threads
+template <int T>
+__device__ __forceinline__ void final_mean(const float* __restrict__ per_sample, int B, float gs, float ls, float* fin,
+                                           float* __restrict__ score) {
+    const int tid = threadIdx.x;
+    float sg = 0.f, sl = 0.f;
+    const float4* p4 = reinterpret_cast<const float4*>(per_sample);
+    const int n2 = B >> 1;   // sample pairs
+    int i = tid;
+    for (; i + 3 * T < n2; i += 4 * T) {
+        const float4 a = __ldcg(p4 + i), b = __ldcg(p4 + i + T), c = __ldcg(p4 + i + 2 * T), d = __ldcg(p4 + i + 3 * T);
+        sg += a.x; sl += a.y; sg += a.z; sl += a.w;
+        sg += b.x; sl += b.y; sg += b.z; sl += b.w;
+        sg += c.x; sl += c.y; sg += c.z; sl += c.w;
+        sg += d.x; sl += d.y; sg += d.z; sl += d.w;
+    }
+    for (; i < n2; i += T) {
+        const float4 a = __ldcg(p4 + i);
+        sg += a.x; sl += a.y; sg += a.z; sl += a.w;
+    }
+    if ((B & 1) && tid == 0) { sg += __ldcg(per_sample + 2 * (B - 1)); sl += __ldcg(per_sample + 2 * (B - 1) + 1); }
+    fin[tid] = gs * sg + ls * sl;
+    __syncthreads();
+    for (int h = T / 2; h > 0; h >>= 1) {
+        if (tid < h) fin[tid] += fin[tid + h];
+        __syncthreads();
+    }
+    if (tid == 0) score[0] = fin[0] / (float)B;
+}
+
 // CH = float4 chunks of the row held per thread (D <= CH * 4 * GROUP)
 template <int GROUP, int CH, int KMAX>
 __global__ void __launch_bounds__(EN_THREADS, CH <= 2 ? 3 : 1)
@@ -204,18 +235,7 @@ energy_kernel(const float* __restrict__ f, const int64_t* __restrict__ target, c
     __syncthreads();
     if (is_last) {
         __threadfence();
-        float sg = 0.f, sl = 0.f;
-        for (int i = threadIdx.x; i < B; i += EN_THREADS) {
-            sg += __ldcg(per_sample + 2 * i);
-            sl += __ldcg(per_sample + 2 * i + 1);
-        }
-        fin[threadIdx.x] = gs * sg + ls * sl;
-        __syncthreads();
-        for (int s = EN_THREADS / 2; s > 0; s >>= 1) {
-            if (threadIdx.x < s) fin[threadIdx.x] += fin[threadIdx.x + s];
-            __syncthreads();
-        }
-        if (threadIdx.x == 0) score[0] = fin[0] / (float)B;
+        final_mean<EN_THREADS>(per_sample, B, gs, ls, fin, score);
     }
 }
 
@@ -311,7 +331,21 @@ class_sort_kernel(const int64_t* __restrict__ target, int B, int C, int* __restr
 // ---------------------------------------------------------------------------------------------------
 // large B: class-sorted tile kernel
 // ---------------------------------------------------------------------------------------------------
-constexpr int ET_R = 4;   // samples per batch (one ring stage)
+// samples per batch (one ring stage).  Measured at B = 65536: 8 rows per batch are slower than 4 for KT >= 5 (0.50 vs 0.59 of the
+// HBM roofline at K = 10, one 8-warp CTA per SM either way) and +3 % for KT <= 4 at the price of one CTA per SM
+#ifndef DD_K4_R_SMALL
+#define DD_K4_R_SMALL 4
+#endif
+#ifndef DD_K4_R_LARGE
+#define DD_K4_R_LARGE 4
+#endif
+#ifndef DD_K4_SPLIT_RS
+#define DD_K4_SPLIT_RS 2
+#endif
+#ifndef DD_K4_SPLIT_MINK
+#define DD_K4_SPLIT_MINK 99   // smallest KT whose group prototypes are split over two thread groups (TileCfg::NG); measured slower, off
+#endif
+__host__ __device__ constexpr int et_rows(int KT) { return KT <= 4 ? DD_K4_R_SMALL : DD_K4_R_LARGE; }
 
 // Warp sum of S packed (float2) partials per lane through a warp-private shared-memory transposition: every lane
 // stores its S partials (STS.64 into tr[slot][lane]); LPS = 32 / pow2(S) lanes then share a slot row, each adds its
@@ -352,34 +386,46 @@ __device__ __forceinline__ float2 tr_reduce(const float2 (&v)[S], float2* tr, in
     return t;
 }
 
+// NG thread groups of 256 threads share a batch.  NG = 1: every thread holds all KT prototype slices (+ g) of its 8 columns
+// (8 (KT+1) registers): KT <= 4 runs two CTAs per SM.  NG = 2 (KT >= 5): the group prototypes are SPLIT over two groups --
+// group 0 holds l_0..l_{KH-1} and reduces <f,g> with them, group 1 holds l_KH..l_{KT-1} and reduces |f|^2, both hold g --
+// so a thread reduces half the values per row, the kernel fits 128 registers and 16 warps (not 8) hide its latencies.
+// The gradient row of a sample is written by the group that holds its l*.
 template <int KT>
 struct TileCfg {
-    static constexpr int R = ET_R;
-    static constexpr int NV = KT + 2;                        // reduced values per row in pass 1: K dots, <f,g>, |f|^2
+    static constexpr int R = et_rows(KT);
+    static constexpr int NG = KT >= DD_K4_SPLIT_MINK ? 2 : 1;
+    static constexpr int THREADS = NG * PK_THREADS;
+    static constexpr int NW = NG * PK_WARPS;
+    static constexpr int KH = KT / NG;                       // group prototypes per thread group
+    static constexpr int NX = NG == 1 ? 2 : 1;               // extra reduced values per row and group: <f,g>, |f|^2
+    static constexpr int NV = KH + NX;                       // reduced values per row and group in pass 1
     static constexpr int SP1 = (NV + 1) / 2;                 // ... packed in pairs
-    static constexpr int RS = (32 / SP1) >= R ? R : (32 / SP1);   // rows per reduction round
+    static constexpr int RS0 = (32 / SP1) >= R ? R : (32 / SP1);
+    static constexpr int RS = (NG == 2 && RS0 > DD_K4_SPLIT_RS) ? DD_K4_SPLIT_RS : RS0;   // rows per reduction round (split kernels: register budget)
     static constexpr int NSUB = (R + RS - 1) / RS;
     static constexpr int S1 = RS * SP1;                      // slots per round
     static constexpr int S2 = R * 2;                         // exact pass: (|fn-g|^2, |fn-l*|^2), (<f,g-fn>, <f,l*-fn>) per row
-    static constexpr int SPN = (KT + 2) / 2;                 // prototype norms: |l_k|^2 (k < KT), |g|^2
+    static constexpr int SPN = (KH + 2) / 2;                 // prototype norms per group: |l_k|^2 (KH of them), |g|^2
     static constexpr int TR_A = TrCfg<S1>::FLOAT2S > TrCfg<S2>::FLOAT2S ? TrCfg<S1>::FLOAT2S : TrCfg<S2>::FLOAT2S;
     static constexpr int TR_FLOAT2S = TR_A > TrCfg<SPN>::FLOAT2S ? TR_A : TrCfg<SPN>::FLOAT2S;
-    static constexpr int CTAS_PER_SM = KT <= 4 ? 2 : 1;
-    static constexpr size_t SMEM_FIXED = PK_MAX_STAGES * sizeof(uint64_t) + (size_t)PK_WARPS * TR_FLOAT2S * sizeof(float2) +
-                                         (size_t)PK_WARPS * (2 * NSUB + 1) * 32 * sizeof(float2);
+    static constexpr int CTAS_PER_SM = (KT <= 4 && R <= 4) ? 2 : 1;
+    static constexpr size_t SMEM_FIXED = PK_MAX_STAGES * sizeof(uint64_t) + (size_t)NW * TR_FLOAT2S * sizeof(float2) +
+                                         (size_t)NW * (2 * NSUB + 1) * 32 * sizeof(float2);
+    static_assert(KT % NG == 0 && SP1 <= 32 && SPN <= 16 && S2 <= 32, "unsupported KT");
 };
 
 // run body(p) with p = the K-th prototype slice, K CTA-uniform: a tree of uniform branches around COPIES of the body,
 // so the selected registers are used in place (a register array cannot be indexed at run time without going through
 // local memory, and copying 8 registers per selection costs as much as the arithmetic that follows)
-template <int KT, int LO, int HI, typename F>
-__device__ __forceinline__ void with_proto(const float4 (&l8)[KT][PK_CH], int k, F&& body) {
+template <int KN, int LO, int HI, typename F>
+__device__ __forceinline__ void with_proto(const float4 (&l8)[KN][PK_CH], int k, F&& body) {
     if constexpr (HI - LO == 1) {
         body(l8[LO]);
     } else {
         constexpr int MID = (LO + HI) / 2;
-        if (k < MID) with_proto<KT, LO, MID>(l8, k, body);
-        else with_proto<KT, MID, HI>(l8, k, body);
+        if (k < MID) with_proto<KN, LO, MID>(l8, k, body);
+        else with_proto<KN, MID, HI>(l8, k, body);
     }
 }
 
@@ -388,41 +434,51 @@ __device__ __forceinline__ float2 hi2(const float4& v) { return make_float2(v.z,
 __device__ __forceinline__ float2 dot4_first(const float4& a, const float4& b) {
     return ffma2(hi2(a), hi2(b), fmul2(lo2(a), lo2(b)));
 }
+__device__ __forceinline__ float dot8(const float4 (&a)[PK_CH], const float4 (&b)[PK_CH]) {
+    float2 s = dot4_first(a[0], b[0]);
+#pragma unroll
+    for (int ch = 1; ch < PK_CH; ++ch) s = dot4(a[ch], b[ch], s);
+    return s.x + s.y;
+}
 
 // One batch = <= R samples of one class.  Per batch and thread (8 owned columns):
-//   pass 1   K dots <f,l_k>, <f,g>, |f|^2 against the register-resident prototype slices -> warp transposition ->
-//            one shared-memory hop across the 8 warps (ONE __syncthreads per batch);
+//   pass 1   the group's dots <f,l_k>, <f,g> / |f|^2 against the register-resident prototype slices -> warp transposition
+//            -> one shared-memory hop across the warps (ONE __syncthreads per batch);
 //   finish   (lane r finishes row r, every warp redundantly) k* = first argmax, s = 1/||f||, and the two distances
 //            from the dots:  ||fn-p||^2 = |fn|^2 - 2 s <f,p> + |p|^2  (|p|^2 reduced once per class run);
 //   exact    only if some distance of the batch is so small that the expansion loses accuracy
 //            (d^2 < (|fn|^2+|p|^2)/8, e.g. f on its prototype): direct sums of (p - fn)^2 like the reference,
 //            one more reduction round + barrier.  CTA-uniform decision;
-//   pass 3   grad = A f + Bg g + Bl l*  (the chain rule through f/||f|| folded into the three coefficients).
+//   pass 3   grad = A f + Bg g + Bl l*  (the chain rule through f/||f|| folded into the three coefficients),
+//            by the thread group that holds l*.
 // FULL: D == 2048 (every thread owns both of its chunks), K == KT, both prototype tables present -> no predicates
 template <int KT, bool FULL>
-__global__ void __launch_bounds__(EN_THREADS, TileCfg<KT>::CTAS_PER_SM)
+__global__ void __launch_bounds__(TileCfg<KT>::THREADS, TileCfg<KT>::CTAS_PER_SM)
 energy_tile_kernel(const float* __restrict__ f, const int* __restrict__ perm, const int* __restrict__ off,
                    const float* __restrict__ g, const float* __restrict__ l, int B, int D_, int C, int K_, float gs, float ls,
                    int normalize_f, float* __restrict__ score, float* __restrict__ per_sample, int32_t* __restrict__ kstar_out,
                    float* __restrict__ grad_f, unsigned int* __restrict__ ticket, int stages) {
     using Cfg = TileCfg<KT>;
-    constexpr int R = Cfg::R, NV = Cfg::NV, SP1 = Cfg::SP1, RS = Cfg::RS, NSUB = Cfg::NSUB, S1 = Cfg::S1, S2 = Cfg::S2, SPN = Cfg::SPN;
-    static_assert(SP1 <= 32, "KT too large");
+    constexpr int R = Cfg::R, NG = Cfg::NG, NW = Cfg::NW, KH = Cfg::KH, NV = Cfg::NV, SP1 = Cfg::SP1, RS = Cfg::RS, NSUB = Cfg::NSUB,
+                  S1 = Cfg::S1, S2 = Cfg::S2, SPN = Cfg::SPN, THREADS = Cfg::THREADS;
     const int D = FULL ? PK_MAX_D : D_;
     const int K = FULL ? KT : K_;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int stage_elems = R * D;
     float* ring = reinterpret_cast<float*>(smem_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)stages * stage_elems * sizeof(float));
-    float2* tr_all = reinterpret_cast<float2*>(full + PK_MAX_STAGES);          // [PK_WARPS][TR_FLOAT2S]
+    float2* tr_all = reinterpret_cast<float2*>(full + PK_MAX_STAGES);          // [NW][TR_FLOAT2S]
     // cross1 is double-buffered by batch parity: with one barrier per batch a fast warp writes the partials of batch
     // i+1 while a slow one still reads those of batch i (it cannot get two batches ahead)
-    float2* cross1_all = tr_all + PK_WARPS * Cfg::TR_FLOAT2S;                 // [2][PK_WARPS][NSUB][32]
-    float2* cross2 = cross1_all + 2 * PK_WARPS * NSUB * 32;                   // [PK_WARPS][32]
-    __shared__ float fin[EN_THREADS];
+    float2* cross1_all = tr_all + NW * Cfg::TR_FLOAT2S;                       // [2][NW][NSUB][32]
+    float2* cross2 = cross1_all + 2 * NW * NSUB * 32;                         // [NW][32]
+    __shared__ float fin[THREADS];
     __shared__ bool is_last;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int grp = NG == 1 ? 0 : tid / PK_THREADS;     // thread group (warp-uniform)
+    const int t = NG == 1 ? tid : tid % PK_THREADS;     // column owner index inside the group
+    const int k0 = grp * KH;                            // first group prototype held by this thread group
     float2* tr = tr_all + warp * Cfg::TR_FLOAT2S;
     const int G = gridDim.x, gi = blockIdx.x;
     const int r0 = (int)((int64_t)B * gi / G), r1 = (int)((int64_t)B * (gi + 1) / G);
@@ -430,7 +486,7 @@ energy_tile_kernel(const float* __restrict__ f, const int* __restrict__ perm, co
     int chunk[PK_CH];
     bool own[PK_CH];
 #pragma unroll
-    for (int ch = 0; ch < PK_CH; ++ch) { chunk[ch] = tid + ch * PK_THREADS; own[ch] = FULL || chunk[ch] < nch; }
+    for (int ch = 0; ch < PK_CH; ++ch) { chunk[ch] = t + ch * PK_THREADS; own[ch] = FULL || chunk[ch] < nch; }
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     const bool has_g = FULL || g != nullptr, has_l = FULL || l != nullptr;
     const float invB = 1.f / (float)B;
@@ -470,8 +526,11 @@ energy_tile_kernel(const float* __restrict__ f, const int* __restrict__ perm, co
             issue(s, bn, lane < bn ? __ldg(perm + br + lane) : 0);
         }
     }
-    float4 g8[PK_CH], l8[KT][PK_CH];
-    float2 pn = make_float2(0.f, 0.f);   // lane q: (|p_2q|^2, |p_2q+1|^2), p = l_0 .. l_KT-1, g
+    float4 g8[PK_CH], l8[KH][PK_CH];
+    // lane q < SPN: (|p_2q|^2, |p_2q+1|^2) of thread group j in pn[j], p = the group's l_k0 .. l_k0+KH-1, then g
+    float2 pn[NG];
+#pragma unroll
+    for (int j = 0; j < NG; ++j) pn[j] = make_float2(0.f, 0.f);
     int cur = -1;
     int s = 0, flip = 0;
     uint32_t parity = 0;
@@ -489,11 +548,11 @@ energy_tile_kernel(const float* __restrict__ f, const int* __restrict__ perm, co
         n_rf_src = lane < n_rf ? __ldg(perm + br + lane) : 0;
     }
     while (n_bn > 0) {
-        const int brow = n_brow, bn = n_bn, bc = n_bc;
+        const int bn = n_bn, bc = n_bc;
         const int orig_l = n_orig;                        // lane r: original index of row r
         const int rf_n = n_rf, rf_src = n_rf_src;
         const bool valid = bc < C;   // bucket C = out-of-range targets
-        float2* cross1 = cross1_all + flip * (PK_WARPS * NSUB * 32);
+        float2* cross1 = cross1_all + flip * (NW * NSUB * 32);
         flip ^= 1;
         if (bc != cur && valid) {   // new class run: prototype slices into registers, their squared norms into `pn`
             cur = bc;
@@ -501,38 +560,31 @@ energy_tile_kernel(const float* __restrict__ f, const int* __restrict__ perm, co
             for (int ch = 0; ch < PK_CH; ++ch) {
                 g8[ch] = (has_g && own[ch]) ? __ldg(reinterpret_cast<const float4*>(g + (int64_t)bc * D) + chunk[ch]) : zero4;
 #pragma unroll
-                for (int k = 0; k < KT; ++k)
-                    l8[k][ch] = (has_l && (FULL || k < K) && own[ch])
-                                    ? __ldg(reinterpret_cast<const float4*>(l + ((int64_t)bc * K + k) * D) + chunk[ch]) : zero4;
+                for (int k = 0; k < KH; ++k)
+                    l8[k][ch] = (has_l && (FULL || k0 + k < K) && own[ch])
+                                    ? __ldg(reinterpret_cast<const float4*>(l + ((int64_t)bc * K + k0 + k) * D) + chunk[ch]) : zero4;
             }
             float nn[2 * SPN];
 #pragma unroll
             for (int j = 0; j < 2 * SPN; ++j) nn[j] = 0.f;
 #pragma unroll
-            for (int k = 0; k < KT; ++k) {
-                float2 a = dot4_first(l8[k][0], l8[k][0]);
-#pragma unroll
-                for (int ch = 1; ch < PK_CH; ++ch) a = dot4(l8[k][ch], l8[k][ch], a);
-                nn[k] = a.x + a.y;
-            }
-            {
-                float2 a = dot4_first(g8[0], g8[0]);
-#pragma unroll
-                for (int ch = 1; ch < PK_CH; ++ch) a = dot4(g8[ch], g8[ch], a);
-                nn[KT] = a.x + a.y;
-            }
+            for (int k = 0; k < KH; ++k) nn[k] = dot8(l8[k], l8[k]);
+            nn[KH] = dot8(g8, g8);
             float2 vn[SPN];
 #pragma unroll
             for (int q = 0; q < SPN; ++q) vn[q] = make_float2(nn[2 * q], nn[2 * q + 1]);
-            const float2 t = tr_reduce<SPN>(vn, tr, lane);
+            const float2 tn = tr_reduce<SPN>(vn, tr, lane);
             __syncthreads();   // cross2 may still be read by a slow warp of the previous batch's exact pass
-            if (lane % TrCfg<SPN>::LPS == 0 && lane / TrCfg<SPN>::LPS < SPN) cross2[warp * 32 + lane / TrCfg<SPN>::LPS] = t;
+            if (lane % TrCfg<SPN>::LPS == 0 && lane / TrCfg<SPN>::LPS < SPN) cross2[warp * 32 + lane / TrCfg<SPN>::LPS] = tn;
             __syncthreads();
-            pn = make_float2(0.f, 0.f);
-            if (lane < SPN) {
-                pn = cross2[lane];
 #pragma unroll
-                for (int w = 1; w < PK_WARPS; ++w) pn = fadd2(pn, cross2[w * 32 + lane]);
+            for (int j = 0; j < NG; ++j) {
+                pn[j] = make_float2(0.f, 0.f);
+                if (lane < SPN) {
+                    pn[j] = cross2[(j * PK_WARPS) * 32 + lane];
+#pragma unroll
+                    for (int w = 1; w < PK_WARPS; ++w) pn[j] = fadd2(pn[j], cross2[(j * PK_WARPS + w) * 32 + lane]);
+                }
             }   // (the next write to cross2 is behind this batch's pass-1 barrier)
         }
         mbar_wait(&full[s], parity);
@@ -546,7 +598,7 @@ energy_tile_kernel(const float* __restrict__ f, const int* __restrict__ perm, co
                 else xv[r][ch] = own[ch] ? *reinterpret_cast<const float4*>(st + r * D + chunk[ch] * 4) : zero4;
             }
 
-        // ---- pass 1: <f,l_k>, <f,g>, |f|^2 of the raw rows, packed in pairs, RS rows per transposition round ----
+        // ---- pass 1: the group's <f,l_k>, then <f,g> and/or |f|^2 of the raw rows, packed in pairs, RS rows per round ----
 #pragma unroll
         for (int h = 0; h < NSUB; ++h) {
             float2 v[S1];
@@ -558,27 +610,21 @@ energy_tile_kernel(const float* __restrict__ f, const int* __restrict__ perm, co
                 for (int j = 0; j < 2 * SP1; ++j) d[j] = 0.f;
                 if (r < R) {
 #pragma unroll
-                    for (int k = 0; k < KT; ++k) {
-                        if (FULL || k < K) {
-                            float2 a = dot4_first(xv[r][0], l8[k][0]);
-#pragma unroll
-                            for (int ch = 1; ch < PK_CH; ++ch) a = dot4(xv[r][ch], l8[k][ch], a);
-                            d[k] = a.x + a.y;
-                        }
-                    }
-                    {
-                        float2 a = dot4_first(xv[r][0], g8[0]), b = dot4_first(xv[r][0], xv[r][0]);
-#pragma unroll
-                        for (int ch = 1; ch < PK_CH; ++ch) { a = dot4(xv[r][ch], g8[ch], a); b = dot4(xv[r][ch], xv[r][ch], b); }
-                        d[KT] = a.x + a.y;
-                        d[KT + 1] = b.x + b.y;
+                    for (int k = 0; k < KH; ++k)
+                        if (FULL || k0 + k < K) d[k] = dot8(xv[r], l8[k]);
+                    if constexpr (NG == 1) {
+                        d[KH] = dot8(xv[r], g8);
+                        d[KH + 1] = dot8(xv[r], xv[r]);
+                    } else {
+                        if (grp == 0) d[KH] = dot8(xv[r], g8);
+                        else d[KH] = dot8(xv[r], xv[r]);
                     }
                 }
 #pragma unroll
                 for (int q = 0; q < SP1; ++q) v[rr * SP1 + q] = make_float2(d[2 * q], d[2 * q + 1]);
             }
-            const float2 t = tr_reduce<S1>(v, tr, lane);
-            if (lane % TrCfg<S1>::LPS == 0 && lane / TrCfg<S1>::LPS < S1) cross1[(warp * NSUB + h) * 32 + lane / TrCfg<S1>::LPS] = t;
+            const float2 tp = tr_reduce<S1>(v, tr, lane);
+            if (lane % TrCfg<S1>::LPS == 0 && lane / TrCfg<S1>::LPS < S1) cross1[(warp * NSUB + h) * 32 + lane / TrCfg<S1>::LPS] = tp;
         }
         __syncthreads();
         // every thread holds the batch in registers: refill the stage
@@ -587,37 +633,49 @@ energy_tile_kernel(const float* __restrict__ f, const int* __restrict__ perm, co
         // ---- finish: lane r < R handles row r (every warp redundantly; no second barrier needed) ----
         const int my_r = lane < R ? lane : 0;
         const int my_h = my_r / RS, my_base = (my_r % RS) * SP1;
-        float dk[2 * SP1];
+        float dk[NG][2 * SP1];
 #pragma unroll
-        for (int j = 0; j < 2 * SP1; ++j) dk[j] = 0.f;
+        for (int j = 0; j < NG; ++j)
+#pragma unroll
+            for (int i = 0; i < 2 * SP1; ++i) dk[j][i] = 0.f;
 #pragma unroll
         for (int h = 0; h < NSUB; ++h) {
-            float2 tot = make_float2(0.f, 0.f);
-            if (lane < S1) {
-                tot = cross1[(0 * NSUB + h) * 32 + lane];
 #pragma unroll
-                for (int w = 1; w < PK_WARPS; ++w) tot = fadd2(tot, cross1[(w * NSUB + h) * 32 + lane]);   // fixed order
-            }
+            for (int j = 0; j < NG; ++j) {
+                float2 tot = make_float2(0.f, 0.f);
+                if (lane < S1) {
+                    tot = cross1[((j * PK_WARPS) * NSUB + h) * 32 + lane];
 #pragma unroll
-            for (int q = 0; q < SP1; ++q) {
-                const float tx = __shfl_sync(0xffffffffu, tot.x, my_base + q), ty = __shfl_sync(0xffffffffu, tot.y, my_base + q);
-                if (NSUB == 1 || my_h == h) { dk[2 * q] = tx; dk[2 * q + 1] = ty; }
+                    for (int w = 1; w < PK_WARPS; ++w) tot = fadd2(tot, cross1[((j * PK_WARPS + w) * NSUB + h) * 32 + lane]);   // fixed order
+                }
+#pragma unroll
+                for (int q = 0; q < SP1; ++q) {
+                    const float tx = __shfl_sync(0xffffffffu, tot.x, my_base + q), ty = __shfl_sync(0xffffffffu, tot.y, my_base + q);
+                    if (NSUB == 1 || my_h == h) { dk[j][2 * q] = tx; dk[j][2 * q + 1] = ty; }
+                }
             }
         }
         int ks = 0;
-        float fl = dk[0];   // <f, l*>
+        float fl = dk[0][0];   // <f, l*>
         if (has_l) {
 #pragma unroll
-            for (int k = 1; k < KT; ++k)
-                if ((FULL || k < K) && dk[k] > fl) { fl = dk[k]; ks = k; }   // strict > : first max wins, like torch.argmax
+            for (int k = 1; k < KT; ++k) {
+                const float dv = dk[k / KH][k % KH];
+                if ((FULL || k < K) && dv > fl) { fl = dv; ks = k; }   // strict > : first max wins, like torch.argmax
+            }
         }
-        const float fg = dk[KT], ff = dk[KT + 1];
+        const float fg = dk[0][KH], ff = NG == 1 ? dk[0][KH + 1] : dk[NG - 1][KH];
         // generate_data.py:747  f / f.norm(dim=-1, keepdim=True): applied as a per-row scale s = 1/||f||
         const float s_l = normalize_f ? rsqrtf(ff) : 1.f;
         const float fn2 = s_l * s_l * ff;                                      // |fn|^2
-        const float nlx = __shfl_sync(0xffffffffu, pn.x, ks >> 1), nly = __shfl_sync(0xffffffffu, pn.y, ks >> 1);
-        const float nl = (ks & 1) ? nly : nlx;                                 // |l*|^2
-        const float ng = __shfl_sync(0xffffffffu, (KT & 1) ? pn.y : pn.x, KT >> 1);   // |g|^2
+        const int kk = ks % KH;                                                // index of l* inside its thread group
+        float nl = 0.f;                                                        // |l*|^2
+#pragma unroll
+        for (int j = 0; j < NG; ++j) {
+            const float nx = __shfl_sync(0xffffffffu, pn[j].x, kk >> 1), ny = __shfl_sync(0xffffffffu, pn[j].y, kk >> 1);
+            if (NG == 1 || ks / KH == j) nl = (kk & 1) ? ny : nx;
+        }
+        const float ng = __shfl_sync(0xffffffffu, (KH & 1) ? pn[0].y : pn[0].x, KH >> 1);   // |g|^2
         float d2g = fmaf(-2.f * s_l, fg, fn2 + ng), d2l = fmaf(-2.f * s_l, fl, fn2 + nl);
         float sg = fmaf(-s_l, fg, fn2), sl = fmaf(-s_l, fl, fn2);              // <fn, fn-g>, <fn, fn-l*>
         const bool row_on = lane < bn && valid;
@@ -626,15 +684,15 @@ energy_tile_kernel(const float* __restrict__ f, const int* __restrict__ perm, co
 #pragma unroll
         for (int r = 0; r < R; ++r) kr[r] = __shfl_sync(0xffffffffu, ks, r);
         if (__any_sync(0xffffffffu, small)) {
-            // ---- exact pass (fn = s f): ||g-fn||^2, ||l*-fn||^2, <f, g-fn>, <f, l*-fn> summed directly ----
+            // ---- exact pass (fn = s f): ||g-fn||^2, ||l*-fn||^2, <f, g-fn>, <f, l*-fn> summed directly, by the group holding l* ----
             float2 w2[S2];
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 float2 aG = make_float2(0.f, 0.f), aL = aG, bG = aG, bL = aG;
                 const float nsr = -__shfl_sync(0xffffffffu, s_l, r);
-                if (r < bn && valid) {
+                if (r < bn && valid && (NG == 1 || kr[r] / KH == grp)) {
                     const float2 m = make_float2(nsr, nsr);
-                    with_proto<KT, 0, KT>(l8, kr[r], [&](const float4 (&p)[PK_CH]) {
+                    with_proto<KH, 0, KH>(l8, kr[r] - k0, [&](const float4 (&p)[PK_CH]) {
 #pragma unroll
                         for (int ch = 0; ch < PK_CH; ++ch) {
                             const float2 x0 = lo2(xv[r][ch]), x1 = hi2(xv[r][ch]);
@@ -648,14 +706,14 @@ energy_tile_kernel(const float* __restrict__ f, const int* __restrict__ perm, co
                 w2[2 * r] = make_float2(aG.x + aG.y, aL.x + aL.y);
                 w2[2 * r + 1] = make_float2(bG.x + bG.y, bL.x + bL.y);
             }
-            const float2 t = tr_reduce<S2>(w2, tr, lane);
-            if (lane % TrCfg<S2>::LPS == 0 && lane / TrCfg<S2>::LPS < S2) cross2[warp * 32 + lane / TrCfg<S2>::LPS] = t;
+            const float2 te = tr_reduce<S2>(w2, tr, lane);
+            if (lane % TrCfg<S2>::LPS == 0 && lane / TrCfg<S2>::LPS < S2) cross2[warp * 32 + lane / TrCfg<S2>::LPS] = te;
             __syncthreads();
             float2 tot2 = make_float2(0.f, 0.f);
             if (lane < S2) {
                 tot2 = cross2[lane];
 #pragma unroll
-                for (int w = 1; w < PK_WARPS; ++w) tot2 = fadd2(tot2, cross2[w * 32 + lane]);
+                for (int w = 1; w < NW; ++w) tot2 = fadd2(tot2, cross2[w * 32 + lane]);
             }
             d2g = __shfl_sync(0xffffffffu, tot2.x, 2 * my_r); d2l = __shfl_sync(0xffffffffu, tot2.y, 2 * my_r);
             sg = -s_l * __shfl_sync(0xffffffffu, tot2.x, 2 * my_r + 1); sl = -s_l * __shfl_sync(0xffffffffu, tot2.y, 2 * my_r + 1);
@@ -674,17 +732,17 @@ energy_tile_kernel(const float* __restrict__ f, const int* __restrict__ perm, co
             per_sample[2 * orig_l + 1] = valid ? dl : bad;
             kstar_out[orig_l] = valid ? ks : 0;
         }
-        // ---- pass 3: gradient rows, written at the samples' original positions ----
+        // ---- pass 3: gradient rows, written at the samples' original positions by the group that holds l* ----
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const float A = __shfl_sync(0xffffffffu, A_l, r), Bg = __shfl_sync(0xffffffffu, Bg_l, r);
             const float Bl = __shfl_sync(0xffffffffu, Bl_l, r);
             const int orig = __shfl_sync(0xffffffffu, orig_l, r);
-            if (r < bn) {
+            if (r < bn && (NG == 1 || (valid ? kr[r] / KH : r % NG) == grp)) {
                 float4* orow = reinterpret_cast<float4*>(grad_f + (size_t)(unsigned)orig * (unsigned)D);
                 if (valid) {
                     const float2 a2 = make_float2(A, A), bg2 = make_float2(Bg, Bg), bl2 = make_float2(Bl, Bl);
-                    with_proto<KT, 0, KT>(l8, kr[r], [&](const float4 (&p)[PK_CH]) {
+                    with_proto<KH, 0, KH>(l8, kr[r] - k0, [&](const float4 (&p)[PK_CH]) {
 #pragma unroll
                         for (int ch = 0; ch < PK_CH; ++ch) {
                             float2 o0 = fmul2(lo2(xv[r][ch]), a2), o1 = fmul2(hi2(xv[r][ch]), a2);
@@ -723,18 +781,413 @@ energy_tile_kernel(const float* __restrict__ f, const int* __restrict__ perm, co
     __syncthreads();
     if (is_last) {
         __threadfence();
-        float sg = 0.f, sl = 0.f;
-        for (int i = tid; i < B; i += EN_THREADS) {
-            sg += __ldcg(per_sample + 2 * i);
-            sl += __ldcg(per_sample + 2 * i + 1);
-        }
-        fin[tid] = gs * sg + ls * sl;
-        __syncthreads();
-        for (int h = EN_THREADS / 2; h > 0; h >>= 1) {
-            if (tid < h) fin[tid] += fin[tid + h];
+        final_mean<THREADS>(per_sample, B, gs, ls, fin, score);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// large B, K <= 10, both tables: warp-PAIR kernel (the default class-tiled mapping)
+// ---------------------------------------------------------------------------------------------------
+// The thread-group kernel above synchronises a whole CTA once per batch and finishes every batch redundantly in every
+// warp: at K = 10 (252 registers, 8 warps per SM) it executes ~1350 warp instructions per sample at 28 % issue-slot
+// utilisation and reaches 0.59 of the HBM roofline.  Here the class's prototype tables live in SHARED memory
+// (g plain, the group prototypes as interleaved PAIRS (l_2p[c], l_2p+1[c]) so that one packed FFMA2 with a broadcast
+// feature advances two dot products and no horizontal add is needed), loaded once per class run of the CTA, and the
+// unit of work is a WARP PAIR: 4 sample rows per batch, warp h of the pair owns the 32-chunk column blocks 2i+h, holds
+// its half of the 4 rows in registers (128) next to 4 x (K/2 + 2) packed accumulators, reduces them with register
+// shuffles only (transposed butterfly), exchanges 4 x (K+2) floats with its partner through shared memory (one
+// 64-thread named barrier), finishes the rows (lane r: row r) and writes its half of the gradient rows.  Pairs never
+// wait for each other inside a class run; each pair has ONE ring stage that is refilled by the TMA engine as soon as
+// both warps hold the batch in registers, i.e. the whole compute phase of a batch hides the next batch's load.
+// Shared memory per sample: (K+1) D 4 / 4 bytes of prototype reads + row + g/l* for the gradient = ~48 KB at K = 10,
+// 53 % of what the SM's shared memory delivers in the time HBM needs for the sample's 16 KB.
+constexpr int EP_R = 4;                      // rows per batch
+constexpr int EP_PAIRS = 4;                  // warp pairs per CTA
+constexpr int EP_THREADS = EP_PAIRS * 64;
+constexpr int EP_CH = 8;                     // float4 chunks per lane -> D <= 2 * 32 * EP_CH * 4 = 2048
+constexpr int EP_MAX_D = 2 * 32 * EP_CH * 4;
+constexpr int EP_NVP = 12;                   // padded values per row in the exchange buffer (K + 2 <= 12)
+constexpr int EP_MAXK = 10;
+
+// 16-byte shared-memory load that the compiler may not narrow: when only two of the four components are used
+// (the l* half of an interleaved prototype pair) it would otherwise emit two LDS.32 at a 16-byte lane stride, a 4-way bank conflict
+__device__ __forceinline__ float4 lds128(const float* p) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
+    return v;
+}
+
+struct PairSmem {
+    size_t table, ring, exch, exch2, pnorm, full, total;
+};
+__host__ __device__ inline PairSmem pair_smem(int D, int KT) {
+    PairSmem s;
+    s.table = 0;                                                   // g [D] | KT/2 x { plane0 [D], plane1 [D] }
+    s.ring = s.table + (size_t)D * (KT + 1) * sizeof(float);       // [EP_PAIRS][EP_R][D]
+    s.exch = s.ring + (size_t)EP_PAIRS * EP_R * D * sizeof(float); // [EP_PAIRS][2][EP_R * EP_NVP]
+    s.exch2 = s.exch + (size_t)EP_PAIRS * 2 * EP_R * EP_NVP * sizeof(float);   // [EP_PAIRS][2][16]
+    s.pnorm = s.exch2 + (size_t)EP_PAIRS * 2 * 16 * sizeof(float); // [16]: |l_k|^2 (k < KT), |g|^2 at [KT]
+    s.full = s.pnorm + 16 * sizeof(float);                         // [EP_PAIRS] mbarriers
+    s.total = s.full + EP_PAIRS * sizeof(uint64_t);
+    return s;
+}
+
+// position cursor of one warp pair over the CTA's class-sorted range [.., r1): batches of <= EP_R rows that never cross a
+// class boundary; inside a class run the batches are dealt round-robin to the EP_PAIRS pairs
+struct PairCursor {
+    int c, b, pos, n;   // class, end of its run (clipped to r1), first row of the batch, rows (0 = exhausted)
+};
+__device__ __forceinline__ void pair_cursor_fix(PairCursor& q, const int* __restrict__ off, int r1, int pair) {
+    while (q.pos >= q.b) {
+        if (q.b >= r1) { q.n = 0; return; }
+        const int a = q.b;
+        do { ++q.c; } while (__ldg(off + q.c + 1) <= a);
+        q.b = min(__ldg(off + q.c + 1), r1);
+        q.pos = a + EP_R * pair;
+    }
+    q.n = min(EP_R, q.b - q.pos);
+}
+
+template <int KT, bool FULLD>
+__global__ void __launch_bounds__(EP_THREADS, 1)
+energy_pair_kernel(const float* __restrict__ f, const int* __restrict__ perm, const int* __restrict__ off,
+                   const float* __restrict__ g, const float* __restrict__ l, int B, int D_, int C, int K, float gs, float ls,
+                   int normalize_f, float* __restrict__ score, float* __restrict__ per_sample, int32_t* __restrict__ kstar_out,
+                   float* __restrict__ grad_f, unsigned int* __restrict__ ticket) {
+    constexpr int KP = KT / 2, NVR = KT + 2, R = EP_R;
+    constexpr int PA = pow2_ge(2 * NVR);                 // values per transposed reduction (two rows)
+    static_assert(KT % 2 == 0 && KT <= EP_MAXK && NVR <= EP_NVP && 2 * NVR <= 32, "unsupported KT");
+    const int D = FULLD ? EP_MAX_D : D_;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const PairSmem lay = pair_smem(D, KT);
+    float* tab_g = reinterpret_cast<float*>(smem_raw + lay.table);
+    float* tab_p = tab_g + D;                                              // pair p: plane0 at p*2D, plane1 at p*2D + D
+    float* ring_all = reinterpret_cast<float*>(smem_raw + lay.ring);
+    float* exch_all = reinterpret_cast<float*>(smem_raw + lay.exch);
+    float* exch2_all = reinterpret_cast<float*>(smem_raw + lay.exch2);
+    float* pnorm = reinterpret_cast<float*>(smem_raw + lay.pnorm);
+    uint64_t* full_all = reinterpret_cast<uint64_t*>(smem_raw + lay.full);
+    __shared__ float fin[EP_THREADS];
+    __shared__ float nred[EP_THREADS / 32][12];
+    __shared__ bool is_last;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int pair = warp >> 1, h = warp & 1;
+    float* ring = ring_all + (size_t)pair * R * D;
+    float* exch = exch_all + pair * (2 * R * EP_NVP);
+    float* exch2 = exch2_all + pair * 32;
+    uint64_t* full = full_all + pair;
+    const int G = gridDim.x, gi = blockIdx.x;
+    const int r0 = (int)((int64_t)B * gi / G), r1 = (int)((int64_t)B * (gi + 1) / G);
+    const int nch = D >> 2;
+    int chunk[EP_CH];
+#pragma unroll
+    for (int i = 0; i < EP_CH; ++i) chunk[i] = (2 * i + h) * 32 + lane;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float invB = 1.f / (float)B;
+    const float bad = __int_as_float(0x7fc00000);
+
+    if (tid < EP_PAIRS) mbar_init(&full_all[tid], 1);
+    if (tid == 0) mbar_fence_init();
+    __syncthreads();
+    pdl_wait();   // perm / off come from the sort kernel launched right before (programmatic dependent launch)
+
+    if (r0 < r1) {
+        // gather the batch's rows through the class-sort permutation: lane i of warp h = 0 copies row i
+        auto issue = [&](int bn, int src) {
+            const uint32_t row_bytes = (uint32_t)D * sizeof(float);
+            if (lane == 0) mbar_expect_tx(full, row_bytes * bn);
+            __syncwarp();
+            if (lane < bn) bulk_g2s(ring + lane * D, f + (int64_t)src * D, row_bytes, full);
+        };
+        const int c_first = find_class(off, C + 1, r0);
+        PairCursor nx;   // the batch AFTER the one in flight; its permutation entries are loaded one batch ahead
+        nx.c = c_first; nx.b = min(__ldg(off + c_first + 1), r1); nx.pos = r0 + R * pair; nx.n = 0;
+        pair_cursor_fix(nx, off, r1, pair);
+        PairCursor cu = nx;
+        int cu_src = lane < cu.n ? __ldg(perm + cu.pos + lane) : 0;     // lane r: original index of row r
+        if (h == 0 && cu.n > 0) issue(cu.n, cu_src);
+        if (cu.n > 0) { nx.pos += R * EP_PAIRS; pair_cursor_fix(nx, off, r1, pair); }
+        int nx_src = lane < nx.n ? __ldg(perm + nx.pos + lane) : 0;
+        uint32_t parity = 0;
+
+        // class runs of the CTA's range, CTA-uniform
+        int rc = c_first, ra = r0, rb = min(__ldg(off + c_first + 1), r1);
+        while (true) {
+            const bool valid = rc < C;   // bucket C = out-of-range targets
+            __syncthreads();             // every pair is done with the previous class's tables
+            if (valid) {
+                // tables of class rc -> shared memory; squared norms on the way
+                float nn[12];
+#pragma unroll
+                for (int j = 0; j < 12; ++j) nn[j] = 0.f;
+                const float4* gsrc = reinterpret_cast<const float4*>(g + (int64_t)rc * D);
+                for (int cc = tid; cc < nch; cc += EP_THREADS) {
+                    const float4 v = __ldg(gsrc + cc);
+                    reinterpret_cast<float4*>(tab_g)[cc] = v;
+                    nn[KT] += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+                }
+#pragma unroll
+                for (int p = 0; p < KP; ++p) {
+                    const float4* la = reinterpret_cast<const float4*>(l + ((int64_t)rc * K + 2 * p) * D);
+                    const float4* lb = reinterpret_cast<const float4*>(l + ((int64_t)rc * K + 2 * p + 1) * D);
+                    const bool ha = 2 * p < K, hb = 2 * p + 1 < K;
+                    float4* p0 = reinterpret_cast<float4*>(tab_p + (size_t)p * 2 * D);
+                    float4* p1 = reinterpret_cast<float4*>(tab_p + (size_t)p * 2 * D + D);
+                    for (int cc = tid; cc < nch; cc += EP_THREADS) {
+                        const float4 a = ha ? __ldg(la + cc) : zero4, b = hb ? __ldg(lb + cc) : zero4;
+                        p0[cc] = make_float4(a.x, b.x, a.y, b.y);
+                        p1[cc] = make_float4(a.z, b.z, a.w, b.w);
+                        nn[2 * p] += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+                        nn[2 * p + 1] += b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j <= KT; ++j) nn[j] = warp_sum(nn[j]);
+                if (lane == 0) {
+#pragma unroll
+                    for (int j = 0; j <= KT; ++j) nred[warp][j] = nn[j];
+                }
+            }
             __syncthreads();
+            if (valid && tid <= KT) {
+                float s = nred[0][tid];
+#pragma unroll
+                for (int w = 1; w < EP_THREADS / 32; ++w) s += nred[w][tid];   // fixed order
+                pnorm[tid] = s;
+            }
+            __syncthreads();
+
+            // ---- the pair's batches of this run ----
+            while (cu.n > 0 && cu.c == rc) {
+                const int bn = cu.n;
+                const int orig_l = cu_src;
+                mbar_wait(full, parity);
+                parity ^= 1;
+                float4 xv[R][EP_CH];
+                float2 accf[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    accf[r] = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int i = 0; i < EP_CH; ++i) {
+                        xv[r][i] = (FULLD || chunk[i] < nch) ? *reinterpret_cast<const float4*>(ring + r * D + chunk[i] * 4) : zero4;
+                        accf[r] = ffma2(lo2(xv[r][i]), lo2(xv[r][i]), accf[r]);       // |f|^2: touches every element, so the
+                        accf[r] = ffma2(hi2(xv[r][i]), hi2(xv[r][i]), accf[r]);       // loads are complete before the refill
+                    }
+                }
+                named_bar_sync(1 + pair, 64);   // both warps hold the batch in registers: refill the pair's stage
+                if (h == 0 && nx.n > 0) issue(nx.n, nx_src);
+
+                float A_l = 0.f, Bg_l = 0.f, Bl_l = 0.f;
+                int ks = 0;
+                if (valid) {
+                    // ---- dots against the shared-memory tables ----
+                    f32x2_t acc[R][KP];
+                    float2 accg[R];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        accg[r] = make_float2(0.f, 0.f);
+#pragma unroll
+                        for (int p = 0; p < KP; ++p) acc[r][p] = 0ull;
+                    }
+#pragma unroll
+                    for (int i = 0; i < EP_CH; ++i) {
+                        if (FULLD || chunk[i] < nch) {
+                            const float4 g4 = reinterpret_cast<const float4*>(tab_g)[chunk[i]];
+#pragma unroll
+                            for (int r = 0; r < R; ++r) {
+                                accg[r] = ffma2(lo2(xv[r][i]), lo2(g4), accg[r]);
+                                accg[r] = ffma2(hi2(xv[r][i]), hi2(g4), accg[r]);
+                            }
+#pragma unroll
+                            for (int p = 0; p < KP; ++p) {
+                                const ulonglong2 u0 = reinterpret_cast<const ulonglong2*>(tab_p + (size_t)p * 2 * D)[chunk[i]];
+                                const ulonglong2 u1 = reinterpret_cast<const ulonglong2*>(tab_p + (size_t)p * 2 * D + D)[chunk[i]];
+#pragma unroll
+                                for (int r = 0; r < R; ++r) {
+                                    acc[r][p] = ffma2_bcast(u0.x, xv[r][i].x, acc[r][p]);
+                                    acc[r][p] = ffma2_bcast(u0.y, xv[r][i].y, acc[r][p]);
+                                    acc[r][p] = ffma2_bcast(u1.x, xv[r][i].z, acc[r][p]);
+                                    acc[r][p] = ffma2_bcast(u1.y, xv[r][i].w, acc[r][p]);
+                                }
+                            }
+                        }
+                    }
+                    // ---- warp totals (two rows per transposed butterfly), exchanged with the partner warp ----
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        float v[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+#pragma unroll
+                        for (int rr = 0; rr < 2; ++rr) {
+                            const int r = 2 * half + rr;
+#pragma unroll
+                            for (int p = 0; p < KP; ++p) {
+                                const float2 a = unpack2(acc[r][p]);
+                                v[rr * NVR + 2 * p] = a.x; v[rr * NVR + 2 * p + 1] = a.y;
+                            }
+                            v[rr * NVR + KT] = accg[r].x + accg[r].y;
+                            v[rr * NVR + KT + 1] = accf[r].x + accf[r].y;
+                        }
+                        xreduce<PA, 16>(v, lane);
+                        const int idx = lane >> (5 - log2i(PA));                    // value index held by this lane
+                        if ((lane & (32 / PA - 1)) == 0 && idx < 2 * NVR) {
+                            const int rr = idx >= NVR ? 1 : 0;
+                            exch[h * (R * EP_NVP) + (2 * half + rr) * EP_NVP + (idx - rr * NVR)] = v[0];
+                        }
+                    }
+                    named_bar_sync(1 + pair, 64);
+                    // ---- finish: lane handles row (lane & 3); both warps compute the same values ----
+                    const int my_r = lane & 3;
+                    float tot[EP_NVP];
+                    {
+                        const float4* e0 = reinterpret_cast<const float4*>(exch + my_r * EP_NVP);
+                        const float4* e1 = reinterpret_cast<const float4*>(exch + R * EP_NVP + my_r * EP_NVP);
+#pragma unroll
+                        for (int q = 0; q < EP_NVP / 4; ++q) {
+                            const float4 a = e0[q], b = e1[q];
+                            tot[4 * q] = a.x + b.x; tot[4 * q + 1] = a.y + b.y; tot[4 * q + 2] = a.z + b.z; tot[4 * q + 3] = a.w + b.w;
+                        }
+                    }
+                    float fl = tot[0];   // <f, l*>
+#pragma unroll
+                    for (int k = 1; k < KT; ++k)
+                        if (k < K && tot[k] > fl) { fl = tot[k]; ks = k; }   // strict > : first max wins, like torch.argmax
+                    const float fg = tot[KT], ff = tot[KT + 1];
+                    // generate_data.py:747  f / f.norm(dim=-1, keepdim=True): applied as a per-row scale s = 1/||f||
+                    const float s_l = normalize_f ? rsqrtf(ff) : 1.f;
+                    const float fn2 = s_l * s_l * ff;                                      // |fn|^2
+                    const float nl = pnorm[ks], ng = pnorm[KT];
+                    float d2g = fmaf(-2.f * s_l, fg, fn2 + ng), d2l = fmaf(-2.f * s_l, fl, fn2 + nl);
+                    float sg = fmaf(-s_l, fg, fn2), sl = fmaf(-s_l, fl, fn2);              // <fn, fn-g>, <fn, fn-l*>
+                    const bool small = my_r < bn && (!(d2g >= 0.125f * (fn2 + ng)) || !(d2l >= 0.125f * (fn2 + nl)));
+                    int kr[R];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) kr[r] = __shfl_sync(0xffffffffu, ks, r);
+                    if (__any_sync(0xffffffffu, small)) {
+                        // ---- exact pass (fn = s f): ||g-fn||^2, ||l*-fn||^2, <f, g-fn>, <f, l*-fn> summed directly ----
+                        float v[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            float2 aG = make_float2(0.f, 0.f), aL = aG, bG = aG, bL = aG;
+                            const float nsr = -__shfl_sync(0xffffffffu, s_l, r);
+                            if (r < bn) {
+                                const float2 m = make_float2(nsr, nsr);
+                                const float* t0 = tab_p + (size_t)(kr[r] >> 1) * 2 * D;
+                                const bool odd = kr[r] & 1;
+#pragma unroll
+                                for (int i = 0; i < EP_CH; ++i) {
+                                    if (FULLD || chunk[i] < nch) {
+                                        const float4 g4 = reinterpret_cast<const float4*>(tab_g)[chunk[i]];
+                                        const float4 u0 = lds128(t0 + chunk[i] * 4), u1 = lds128(t0 + D + chunk[i] * 4);
+                                        const float2 p0 = odd ? make_float2(u0.y, u0.w) : make_float2(u0.x, u0.z);
+                                        const float2 p1 = odd ? make_float2(u1.y, u1.w) : make_float2(u1.x, u1.z);
+                                        const float2 x0 = lo2(xv[r][i]), x1 = hi2(xv[r][i]);
+                                        const float2 dg0 = ffma2(x0, m, lo2(g4)), dg1 = ffma2(x1, m, hi2(g4));
+                                        const float2 dl0 = ffma2(x0, m, p0), dl1 = ffma2(x1, m, p1);
+                                        aG = ffma2(dg0, dg0, aG); aL = ffma2(dl0, dl0, aL); bG = ffma2(x0, dg0, bG); bL = ffma2(x0, dl0, bL);
+                                        aG = ffma2(dg1, dg1, aG); aL = ffma2(dl1, dl1, aL); bG = ffma2(x1, dg1, bG); bL = ffma2(x1, dl1, bL);
+                                    }
+                                }
+                            }
+                            v[4 * r] = aG.x + aG.y; v[4 * r + 1] = aL.x + aL.y; v[4 * r + 2] = bG.x + bG.y; v[4 * r + 3] = bL.x + bL.y;
+                        }
+                        xreduce<16, 16>(v, lane);
+                        if ((lane & 1) == 0) exch2[h * 16 + (lane >> 1)] = v[0];
+                        named_bar_sync(1 + pair, 64);
+                        const float4 a = reinterpret_cast<const float4*>(exch2)[my_r], b = reinterpret_cast<const float4*>(exch2 + 16)[my_r];
+                        d2g = a.x + b.x; d2l = a.y + b.y;
+                        sg = -s_l * (a.z + b.z); sl = -s_l * (a.w + b.w);
+                    }
+                    // 1/d through rsqrt (<= 2 ulp): d = d2 * rsqrt(d2);  d||v||/dv = v/||v||, 0 at v = 0 (torch.norm's sub-gradient)
+                    const float ig = d2g > 0.f ? rsqrtf(d2g) : 0.f, il = d2l > 0.f ? rsqrtf(d2l) : 0.f;
+                    const float dg = d2g * ig, dl = d2l * il;
+                    const float cg = gs * invB * ig, cl = ls * invB * il;
+                    // d score/d fn = cg (fn-g) + cl (fn-l*);  chained through fn = f/||f||:  (that - fn <fn, that>) / ||f||.
+                    // Everything is linear in (f, g, l*):  grad = A f + Bg g + Bl l*
+                    const float sd = normalize_f ? cg * sg + cl * sl : 0.f;
+                    A_l = (cg + cl - sd) * s_l * s_l; Bg_l = -cg * s_l; Bl_l = -cl * s_l;
+                    if (h == 0 && lane < bn) {
+                        per_sample[2 * orig_l] = dg;
+                        per_sample[2 * orig_l + 1] = dl;
+                        kstar_out[orig_l] = ks;
+                    }
+                    // ---- gradient rows (this warp's column blocks), written at the samples' original positions ----
+                    float cA[R], cG[R], cL[R];
+                    const float* tl[R];
+                    bool odd[R];
+                    float4* orow[R];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        cA[r] = __shfl_sync(0xffffffffu, A_l, r); cG[r] = __shfl_sync(0xffffffffu, Bg_l, r);
+                        cL[r] = __shfl_sync(0xffffffffu, Bl_l, r);
+                        const int orig = __shfl_sync(0xffffffffu, orig_l, r);
+                        orow[r] = reinterpret_cast<float4*>(grad_f + (size_t)(unsigned)orig * (unsigned)D);
+                        tl[r] = tab_p + (size_t)(kr[r] >> 1) * 2 * D;
+                        odd[r] = kr[r] & 1;
+                    }
+#pragma unroll
+                    for (int i = 0; i < EP_CH; ++i) {
+                        if (FULLD || chunk[i] < nch) {
+                            const float4 g4 = reinterpret_cast<const float4*>(tab_g)[chunk[i]];
+#pragma unroll
+                            for (int r = 0; r < R; ++r) {
+                                if (r < bn) {
+                                    const float4 u0 = lds128(tl[r] + chunk[i] * 4), u1 = lds128(tl[r] + D + chunk[i] * 4);
+                                    const float2 p0 = odd[r] ? make_float2(u0.y, u0.w) : make_float2(u0.x, u0.z);
+                                    const float2 p1 = odd[r] ? make_float2(u1.y, u1.w) : make_float2(u1.x, u1.z);
+                                    const float2 a2 = make_float2(cA[r], cA[r]), bg2 = make_float2(cG[r], cG[r]), bl2 = make_float2(cL[r], cL[r]);
+                                    float2 o0 = fmul2(lo2(xv[r][i]), a2), o1 = fmul2(hi2(xv[r][i]), a2);
+                                    o0 = ffma2(lo2(g4), bg2, o0); o1 = ffma2(hi2(g4), bg2, o1);
+                                    o0 = ffma2(p0, bl2, o0); o1 = ffma2(p1, bl2, o1);
+                                    orow[r][chunk[i]] = make_float4(o0.x, o0.y, o1.x, o1.y);
+                                }
+                            }
+                        }
+                    }
+                } else {
+                    // out-of-range target: poison the score and the gradient row (NaN), loudly
+                    if (h == 0 && lane < bn) {
+                        per_sample[2 * orig_l] = bad;
+                        per_sample[2 * orig_l + 1] = bad;
+                        kstar_out[orig_l] = 0;
+                    }
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const int orig = __shfl_sync(0xffffffffu, orig_l, r);
+                        if (r < bn) {
+                            float4* orow = reinterpret_cast<float4*>(grad_f + (size_t)(unsigned)orig * (unsigned)D);
+#pragma unroll
+                            for (int i = 0; i < EP_CH; ++i)
+                                if (FULLD || chunk[i] < nch) orow[chunk[i]] = make_float4(bad, bad, bad, bad);
+                        }
+                    }
+                }
+                // next batch; its successor's permutation entries are requested now and used one batch later
+                cu = nx; cu_src = nx_src;
+                if (nx.n > 0) { nx.pos += R * EP_PAIRS; pair_cursor_fix(nx, off, r1, pair); }
+                nx_src = lane < nx.n ? __ldg(perm + nx.pos + lane) : 0;
+            }
+            // next class run of the CTA
+            if (rb >= r1) break;
+            ra = rb;
+            do { ++rc; } while (__ldg(off + rc + 1) <= ra);
+            rb = min(__ldg(off + rc + 1), r1);
         }
-        if (tid == 0) score[0] = fin[0] / (float)B;
+    }
+
+    // ---- deterministic batch mean by the last CTA (sample index order) ----
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) is_last = atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1;  // wraps back to 0
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        final_mean<EP_THREADS>(per_sample, B, gs, ls, fin, score);
     }
 }
 
@@ -775,44 +1228,67 @@ static int launch_energy(const float* f, const int64_t* target, const float* g, 
     return 0;
 }
 
+// class bucketing (memset + one kernel) on `st`; the tile kernels are launched behind it with programmatic dependent launch
+static int launch_class_sort(const int64_t* target, int B, int C, unsigned char* ws, cudaStream_t st) {
+    const EnergyWs w = energy_ws(B, C);
+    unsigned int* ticket2 = (unsigned int*)(ws + w.ticket2_off);
+    // ticket2 (the sort kernel's grid-barrier counter) sits right before counts: one memset clears both
+    DD_CUDA_OK(cudaMemsetAsync(ticket2, 0, (size_t)(w.counts_off - w.ticket2_off) + ((size_t)C + 1) * sizeof(int), st));
+    unsigned pg = (unsigned)((B + EN_THREADS - 1) / EN_THREADS);
+    if (pg > 2u * (unsigned)sm_count()) pg = 2u * (unsigned)sm_count();   // co-resident: the kernel has a grid barrier
+    class_sort_kernel<<<pg, EN_THREADS, 0, st>>>(target, B, C, (int*)(ws + w.counts_off), (int*)(ws + w.rank_off), (int*)(ws + w.off_off),
+                                                 (int*)(ws + w.perm_off), ticket2);
+    DD_LAUNCH_OK();
+    return 0;
+}
+
+template <typename Kern, typename... Args>
+static int launch_pdl(Kern kern, int grid, int block, size_t smem, cudaStream_t st, Args... args) {
+    DD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // programmatic dependent launch behind the sort kernel: barrier init and scheduling overlap its tail
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    DD_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, args...));
+    return 0;
+}
+
 template <int KT>
 static int launch_energy_tile(const float* f, const int64_t* target, const float* g, const float* l, int B, int D, int C, int K,
                               float gs, float ls, int normalize_f, float* score, float* per_sample, int32_t* kstar,
                               float* grad_f, unsigned char* ws, cudaStream_t st) {
     const EnergyWs w = energy_ws(B, C);
-    unsigned int* ticket = (unsigned int*)(ws + w.ticket_off);
-    unsigned int* ticket2 = (unsigned int*)(ws + w.ticket2_off);
-    int* counts = (int*)(ws + w.counts_off);
-    int* off = (int*)(ws + w.off_off);
-    int* rank = (int*)(ws + w.rank_off);
-    int* perm = (int*)(ws + w.perm_off);
-    // ticket2 (the sort kernel's grid-barrier counter) sits right before counts: one memset clears both
-    DD_CUDA_OK(cudaMemsetAsync(ticket2, 0, (size_t)(w.counts_off - w.ticket2_off) + ((size_t)C + 1) * sizeof(int), st));
-    unsigned pg = (unsigned)((B + EN_THREADS - 1) / EN_THREADS);
-    if (pg > 2u * (unsigned)sm_count()) pg = 2u * (unsigned)sm_count();   // co-resident: the kernel has a grid barrier
-    class_sort_kernel<<<pg, EN_THREADS, 0, st>>>(target, B, C, counts, rank, off, perm, ticket2);
-    DD_LAUNCH_OK();
+    if (int rc = launch_class_sort(target, B, C, ws, st)) return rc;
     using Cfg = TileCfg<KT>;
     const size_t ring_bytes = (Cfg::CTAS_PER_SM == 2 ? 100 * 1024 : 208 * 1024) - Cfg::SMEM_FIXED;
-    int stages = (int)(ring_bytes / ((size_t)ET_R * D * sizeof(float)));
+    int stages = (int)(ring_bytes / ((size_t)Cfg::R * D * sizeof(float)));
     if (stages > PK_MAX_STAGES) stages = PK_MAX_STAGES;
     DD_REQUIRE(stages >= 2, DD_EUNSUPPORTED, "dd_energy_fwd_bwd: D=%d too large for the shared-memory ring", D);
-    const size_t smem = (size_t)stages * ET_R * D * sizeof(float) + Cfg::SMEM_FIXED;
+    const size_t smem = (size_t)stages * Cfg::R * D * sizeof(float) + Cfg::SMEM_FIXED;
     const bool full = D == PK_MAX_D && K == KT && g && l;
     auto kern = full ? energy_tile_kernel<KT, true> : energy_tile_kernel<KT, false>;
-    DD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int G = Cfg::CTAS_PER_SM * sm_count();
-    if (G > (B + ET_R - 1) / ET_R) G = (B + ET_R - 1) / ET_R;
-    // programmatic dependent launch behind the sort kernel: barrier init and scheduling overlap its tail
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(G); cfg.blockDim = dim3(EN_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    DD_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, f, (const int*)perm, (const int*)off, g, l, B, D, C, K, gs, ls, normalize_f, score, per_sample,
-                                  kstar, grad_f, ticket, stages));
-    return 0;
+    if (G > (B + Cfg::R - 1) / Cfg::R) G = (B + Cfg::R - 1) / Cfg::R;
+    return launch_pdl(kern, G, Cfg::THREADS, smem, st, f, (const int*)(ws + w.perm_off), (const int*)(ws + w.off_off), g, l, B, D, C, K, gs,
+                      ls, normalize_f, score, per_sample, kstar, grad_f, (unsigned int*)(ws + w.ticket_off), stages);
+}
+
+template <int KT>
+static int launch_energy_pair(const float* f, const int64_t* target, const float* g, const float* l, int B, int D, int C, int K,
+                              float gs, float ls, int normalize_f, float* score, float* per_sample, int32_t* kstar,
+                              float* grad_f, unsigned char* ws, cudaStream_t st) {
+    const EnergyWs w = energy_ws(B, C);
+    if (int rc = launch_class_sort(target, B, C, ws, st)) return rc;
+    const size_t smem = pair_smem(D, KT).total;
+    auto kern = D == EP_MAX_D ? energy_pair_kernel<KT, true> : energy_pair_kernel<KT, false>;
+    int G = sm_count();
+    const int batches = (B + EP_R * EP_PAIRS - 1) / (EP_R * EP_PAIRS);
+    if (G > batches) G = batches;
+    return launch_pdl(kern, G, EP_THREADS, smem, st, f, (const int*)(ws + w.perm_off), (const int*)(ws + w.off_off), g, l, B, D, C, K, gs, ls,
+                      normalize_f, score, per_sample, kstar, grad_f, (unsigned int*)(ws + w.ticket_off));
 }
 
 // smallest B the class-tiled kernel takes in auto mode: below it the class bucketing (a memset + one small kernel) costs
@@ -835,19 +1311,30 @@ extern "C" int dd_energy_fwd_bwd(const float* f, const int64_t* target, const fl
     DD_REQUIRE(D % 4 == 0, DD_EUNSUPPORTED, "dd_energy_fwd_bwd: D=%d must be a multiple of 4", D);
     DD_REQUIRE(!l || (K >= 1 && K <= dd::EN_MAXK), DD_EUNSUPPORTED, "dd_energy_fwd_bwd: K=%d outside 1..%d", K, dd::EN_MAXK);
     DD_REQUIRE(D <= 8192, DD_EUNSUPPORTED, "dd_energy_fwd_bwd: D=%d > 8192", D);
-    DD_REQUIRE(dd::aligned16(f) && dd::aligned16(g) && dd::aligned16(l) && dd::aligned16(grad_f) && dd::aligned16(ws), DD_EINVAL,
+    DD_REQUIRE(dd::aligned16(f) && dd::aligned16(g) && dd::aligned16(l) && dd::aligned16(grad_f) && dd::aligned16(ws) && dd::aligned16(per_sample), DD_EINVAL,
                "dd_energy_fwd_bwd: pointers must be 16-byte aligned");
     DD_REQUIRE(ws_bytes >= 16, DD_EWORKSPACE, "dd_energy_fwd_bwd: workspace %zu < 16 bytes", ws_bytes);
     cudaStream_t st = (cudaStream_t)stream;
     if (!l) K = 0;
     unsigned int* ticket = (unsigned int*)ws;
     // large B: bucket by class and run the tile kernel (needs the full workspace); otherwise one CTA per sample
-    DD_REQUIRE(mode >= 0 && mode <= 2, DD_EINVAL, "dd_energy_fwd_bwd: mode %d (0 auto, 1 per-sample, 2 class-tiled)", mode);
+    DD_REQUIRE(mode >= 0 && mode <= 4, DD_EINVAL, "dd_energy_fwd_bwd: mode %d (0 auto, 1 per-sample, 2 class-tiled, 3 class-tiled / "
+               "thread-group kernel, 4 class-tiled / warp-pair kernel)", mode);
     const bool tile_ok = D <= dd::PK_MAX_D && ws_bytes >= dd::energy_ws(B, C).total;
-    DD_REQUIRE(mode != 2 || tile_ok, DD_EUNSUPPORTED, "dd_energy_fwd_bwd: class-tiled kernel needs D <= %d and a %zu-byte workspace",
+    DD_REQUIRE(mode < 2 || tile_ok, DD_EUNSUPPORTED, "dd_energy_fwd_bwd: class-tiled kernel needs D <= %d and a %zu-byte workspace",
                dd::PK_MAX_D, dd::energy_ws(B, C).total);
-    if (mode == 2 || (mode == 0 && tile_ok && B >= dd::tile_min_b(K))) {
+    const bool pair_ok = g && l && K <= dd::EP_MAXK;
+    DD_REQUIRE(mode != 4 || pair_ok, DD_EUNSUPPORTED, "dd_energy_fwd_bwd: the warp-pair kernel needs both tables and K <= %d", dd::EP_MAXK);
+    if (mode >= 2 || (mode == 0 && tile_ok && B >= dd::tile_min_b(K))) {
 #define ARGS f, target, g, l, B, D, C, K, gs, ls, normalize_f, score, per_sample, kstar, grad_f, (unsigned char*)ws, st
+        // warp-pair kernel (tables in shared memory, 16 rows per CTA in flight) from 64 samples per SM; below that the
+        // thread-group kernel's finer granularity (4 rows per CTA, 2 CTAs per SM for K <= 4) wins
+        if (mode == 4 || (mode != 3 && pair_ok && B >= 64 * dd::sm_count())) {
+            if (K <= 4) return dd::launch_energy_pair<4>(ARGS);
+            if (K <= 6) return dd::launch_energy_pair<6>(ARGS);
+            if (K <= 8) return dd::launch_energy_pair<8>(ARGS);
+            return dd::launch_energy_pair<10>(ARGS);
+        }
         if (K <= 3) return dd::launch_energy_tile<3>(ARGS);
         if (K <= 4) return dd::launch_energy_tile<4>(ARGS);
         if (K <= 6) return dd::launch_energy_tile<6>(ARGS);

@@ -301,14 +301,16 @@ def targets_tensor(targets, C_: int, device) -> torch.Tensor:
     return torch.tensor(ts, dtype=torch.int64, device=device)
 
 
-ENERGY_MODES = {"auto": 0, "sample": 1, "tile": 2}
+ENERGY_MODES = {"auto": 0, "sample": 1, "tile": 2, "tile_cta": 3, "tile_pair": 4}
 
 
 def energy_fwd_bwd(f: torch.Tensor, targets, g: Optional[torch.Tensor], l: Optional[torch.Tensor], gs: float, ls: float,
                    normalize_f: bool = False, mode: str = "auto"):
     """(score[0-dim f32], per_sample [B,2], kstar [B] i32, d score/d f [B,D]) -- forward AND analytic gradient.
     generate_data.py:707-717 (normalize_f=False) / :747-759 (True).  ``mode``: "auto" (by size), "sample" (one CTA per
-    sample, one launch) or "tile" (class-bucketed persistent kernel for large batches)."""
+    sample, one launch), "tile" (class-bucketed persistent kernels for large batches; picks between the next two),
+    "tile_cta" (thread-group kernel, tables in registers: any K / missing table, best below ~64 samples per SM) or
+    "tile_pair" (warp-pair kernel, tables in shared memory: K <= 10 and both tables, the large-batch kernel)."""
     f = _req(f, "image_features", torch.float32)
     if f.dim() != 2:
         raise DistDiffError("image_features must be [B, D]")
@@ -335,7 +337,7 @@ def energy_fwd_bwd(f: torch.Tensor, targets, g: Optional[torch.Tensor], l: Optio
     grad = torch.empty_like(f)
     ws = _energy_workspace(f.device, B, Cn)
     # algorithmic bytes (compulsory HBM traffic): f read + grad written + the prototype tables once
-    tiled = mode == "tile" or (mode == "auto" and D <= 2048 and
+    tiled = mode in ("tile", "tile_cta", "tile_pair") or (mode == "auto" and D <= 2048 and
                                B >= (7 if K >= 5 else 16) * torch.cuda.get_device_properties(f.device).multi_processor_count)
     _call("dd_energy_fwd_bwd", 2 * B * D * 4 + (int(g is not None) + (K if l is not None else 0)) * Cn * D * 4, 3 if tiled else 1,
           _ptr(f), _ptr(y), _ptr(g), _ptr(l), B, D, Cn, K, float(gs), float(ls),

@@ -115,7 +115,9 @@ int dd_image_to_uint8(const void* img, int64_t B, int C, int H, int W, int dtype
  * workspace per stream.  >= 16 bytes always works (one CTA per sample); with dd_energy_workspace_bytes(B, C)
  * bytes a large batch (B >= 16 x #SMs, or 7 x #SMs for K >= 5; D <= 2048) is bucketed by class and runs the class-tiled kernel (prototype
  * slices in registers, sample rows gathered by TMA) -- same results, HBM-bound instead of L2-bound.
- * mode: 0 = choose by size, 1 = one CTA per sample, 2 = class-tiled (needs the full workspace). */
+ * mode: 0 = choose by size, 1 = one CTA per sample, 2 = class-tiled (needs the full workspace; picks 3 or 4 by size), 3 = class-tiled,
+ * thread-group kernel (tables in registers, any K), 4 = class-tiled, warp-pair kernel (tables in shared memory; both tables, K <= 10).
+ * per_sample must be 16-byte aligned. */
 size_t dd_energy_workspace_bytes(int B, int C);
 int dd_energy_fwd_bwd(const float* f, const int64_t* target, const float* g, const float* l, int B, int D, int C,
                       int K, float gs, float ls, int normalize_f, float* score, float* per_sample, int32_t* kstar,

@@ -203,14 +203,15 @@ def _energy_case(B, C, K, D, seed, dup=False):
                                      (5, 4, 1, 512), (1024, 100, 3, 2048), (2000, 50, 10, 2048), (1500, 7, 5, 512),
                                      (64, 1000, 3, 2048)])   # last: ImageNet-scale tables, BASELINE configs[4]
 @pytest.mark.parametrize("normalize_f", [False, True])
-@pytest.mark.parametrize("mode", ["sample", "tile"])   # one CTA per sample / class-bucketed tile kernel (large-B path)
+@pytest.mark.parametrize("mode", ["sample", "tile_cta", "tile_pair"])   # one CTA per sample / class-bucketed kernels (large-B path): thread groups, warp pairs
 def test_energy_vs_oracle(ops, cuda_device, B, C, K, D, normalize_f, mode):
     f, gp, lp, y = _energy_case(B, C, K, D, 10 + B)
     for G, L in ((gp, lp), (gp, None), (None, lp)):
         s_ref, per_ref, k_ref, g_ref = energy.energy_fwd_bwd(f.numpy(), y, None if G is None else G.numpy(),
                                                              None if L is None else L.numpy(), 0.7, 1.3, normalize_f)
+        m = "tile" if mode == "tile_pair" and (G is None or L is None) else mode   # the warp-pair kernel needs both tables
         score, per, kstar, grad = ops.energy_fwd_bwd(f.to(cuda_device), y, None if G is None else G.to(cuda_device),
-                                                     None if L is None else L.to(cuda_device), 0.7, 1.3, normalize_f, mode=mode)
+                                                     None if L is None else L.to(cuda_device), 0.7, 1.3, normalize_f, mode=m)
         assert abs(float(score) - float(s_ref)) <= 1e-5 * abs(float(s_ref))
         assert np.allclose(per.cpu().numpy(), per_ref, rtol=1e-5, atol=1e-6)
         if L is not None:
@@ -264,14 +265,16 @@ def test_energy_tile_matches_sample_kernel(ops, cuda_device, K):
         b = ops.energy_fwd_bwd(*args, nf, mode="auto")
         c = ops.energy_fwd_bwd(*args, nf, mode="tile")
         assert torch.equal(b[0], c[0]) and torch.equal(b[3], c[3])        # auto == tile, bit for bit
-        assert abs(float(a[0]) - float(b[0])) <= 2e-6 * abs(float(a[0]))
-        assert torch.allclose(a[1], b[1], rtol=2e-6, atol=1e-7)
-        assert (a[2] != b[2]).float().mean() < 1e-3                         # only fp32-level argmax ties may differ
-        assert (a[3] - b[3]).norm() <= 2e-6 * a[3].norm()
+        for b in (c, ops.energy_fwd_bwd(*args, nf, mode="tile_cta"), *([ops.energy_fwd_bwd(*args, nf, mode="tile_pair")] if K <= 10 else [])):
+            assert abs(float(a[0]) - float(b[0])) <= 2e-6 * abs(float(a[0]))
+            assert torch.allclose(a[1], b[1], rtol=2e-6, atol=1e-7)
+            assert (a[2] != b[2]).float().mean() < 1e-3                     # only fp32-level argmax ties may differ
+            assert (a[3] - b[3]).norm() <= 2e-6 * a[3].norm()
 
 
+@pytest.mark.parametrize("mode", ["tile_pair", "tile_cta"])
 @pytest.mark.parametrize("normalize_f", [False, True])
-def test_energy_tile_small_distances_take_the_exact_pass(ops, cuda_device, normalize_f):
+def test_energy_tile_small_distances_take_the_exact_pass(ops, cuda_device, normalize_f, mode):
     """Samples on / next to their prototypes: the tile kernel's distance-from-dots expansion would lose accuracy there,
     so the batch falls back to direct sums -- distances, score and gradient still match the oracle, exact zeros included."""
     B, C, K, D = 257, 9, 4, 2048
@@ -285,7 +288,7 @@ def test_energy_tile_small_distances_take_the_exact_pass(ops, cuda_device, norma
     f[40:80] = (lp[yt[40:80], 1] + 3e-2 * torch.randn(40, D, generator=_g(6)) / D ** 0.5) * scale
     s_ref, per_ref, k_ref, g_ref = energy.energy_fwd_bwd(f.numpy(), y, gp.numpy(), lp.numpy(), 1.0, 1.0, normalize_f)
     score, per, kstar, grad = ops.energy_fwd_bwd(f.to(cuda_device), y, gp.to(cuda_device), lp.to(cuda_device), 1.0, 1.0,
-                                                 normalize_f, mode="tile")
+                                                 normalize_f, mode=mode)
     assert abs(float(score) - float(s_ref)) <= 1e-5 * abs(float(s_ref))
     assert np.allclose(per.cpu().numpy()[2:], per_ref[2:], rtol=2e-5, atol=1e-6)
     assert np.allclose(per.cpu().numpy()[:2], per_ref[:2], rtol=1e-5, atol=2e-6)     # ~0 entries: fp32 rounding of fn
@@ -306,7 +309,7 @@ def test_energy_tile_bad_target_is_poisoned(ops, cuda_device):
     yt = torch.tensor(y, dtype=torch.int64)
     yt[7] = C
     yt[200] = -1
-    for mode in ("sample", "tile"):
+    for mode in ("sample", "tile_cta", "tile_pair"):
         score, per, kstar, grad = ops.energy_fwd_bwd(f.to(cuda_device), yt.to(cuda_device), gp.to(cuda_device), lp.to(cuda_device),
                                                      1.0, 1.0, False, mode=mode)
         assert torch.isnan(score) and torch.isnan(grad[7]).all() and torch.isnan(grad[200]).all()

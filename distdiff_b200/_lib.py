@@ -52,6 +52,7 @@ SIGNATURES = {
     "dd_peer_connect": (_i, [_p, _p]),
     "dd_peer_local": (_p, [_p]),
     "dd_peer_header_bytes": (_z, []),
+    "dd_peer_arena_bytes": (_z, [_i, _i, _i]),
     "dd_peer_kmeans_exchange": (_i, [_p, _z, _z, _z, _z, _z, _i, _i, _p]),
     "dd_peer_status": (_i, [_p, _p, C.POINTER(_i)]),
     "dd_peer_timing": (_i, [_p, _p, C.POINTER(C.c_double)]),

@@ -471,8 +471,9 @@ class KMeansBuffers:
         self.ws = proto_workspace(D, C_, K, device)
 
     @staticmethod
-    def arena_bytes(D: int, C_: int, K: int) -> int:
-        return C_ * K * (D * 12 + 20) + 5 * 256
+    def arena_bytes(D: int, C_: int, K: int, world: int = 1) -> int:
+        """Arena bytes behind the header: the five exchanged buffers + the exchange kernel's inbox at the tail."""
+        return int(_lib.lib().dd_peer_arena_bytes(C_ * K, D, world))
 
 
 def kmeans_assign_accum(x_sorted: torch.Tensor, class_off: torch.Tensor, buf: KMeansBuffers, want_inertia: bool = False,

@@ -65,8 +65,8 @@ def sweep(colls, n=100_000, d=2048, classes=100, ks=(3, 5, 10), iters=20, reps=3
             arena = getattr(coll, "arena", None)
             if arena is not None:   # where the last fused exchange spent its time on this rank (device globaltimer)
                 t = arena.timing()
-                rec["exchange_phases_us_rank0"] = {"local_slot_reduce": round(t[1], 1), "flag_barrier_A": round(t[2] - t[1], 1),
-                                                   "owned_rows_reduce_store": round(t[3] - t[2], 1), "flag_barrier_B": round(t[4] - t[3], 1),
+                rec["exchange_phases_us_rank0"] = {"cta0_slot_reduce_push": round(t[1], 1), "cta0_first_owned_row_in_inbox": round(t[2] - t[1], 1),
+                                                   "owned_rows_update_store_all_ctas": round(t[3] - t[2], 1), "flag_barrier_B": round(t[4] - t[3], 1),
                                                    "kernel_total": round(t[4], 1)}
             out.append(rec)
     return {"config": f"k-means prototype sweep, N={n} x D={d}, C={classes}, {iters} Lloyd iterations (BASELINE configs[3])",

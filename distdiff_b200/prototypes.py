@@ -130,9 +130,10 @@ def make_collective(prefer_peer: bool = True):
 
 
 class PeerCollective(NcclCollective):
-    """NcclCollective whose per-iteration k-means exchange is the fused peer-memory kernel (csrc/dd_peer.cu): flag
-    barrier + reduce-scatter by NVLink loads in rank order + centroid update + all-gather of fp32 centroid rows by
-    NVLink stores, one launch per rank, instead of an NCCL all-reduce of fp64 sums followed by the update kernel.
+    """NcclCollective whose per-iteration k-means exchange is the fused peer-memory kernel (csrc/dd_peer.cu):
+    reduce-scatter by NVLink stores into the owners' inboxes + per-row flags, sums in rank order + centroid update by the
+    owner, all-gather of fp32 centroid rows by NVLink stores, flag barrier -- one launch per rank, instead of an NCCL
+    all-reduce of fp64 sums followed by the update kernel.
     The one-off class-sum all-reduce and the ragged all-gathers stay on NCCL."""
 
     def __init__(self):
@@ -145,7 +146,7 @@ class PeerCollective(NcclCollective):
         return out
 
     def kmeans_buffers(self, N, D, C_, K, device):
-        need = ops.KMeansBuffers.arena_bytes(D, C_, K)
+        need = ops.KMeansBuffers.arena_bytes(D, C_, K, self.world)
         if self.arena is not None and self.arena.capacity >= need:
             self.arena.reset()           # same arena, same offsets on every rank (all ranks make the same calls)
         else:

@@ -186,13 +186,15 @@ int dd_comm_allreduce(void* comm, double* sum, size_t n_sum, int64_t* cnt, size_
 int dd_comm_destroy(void* comm);
 
 /* ---- fused centroid exchange over NVLink peer memory (csrc/dd_peer.cu) --------------------------------
- * The per-iteration exchange of the sharded k-means as ONE kernel per rank: flag barrier, reduce-scatter of the
- * partial sums / counts by peer loads in rank order, centroid + norm (dd_kmeans_update's arithmetic), all-gather of
- * the fp32 centroid rows by peer stores, flag barrier.  Replaces dd_comm_allreduce + dd_kmeans_update.
+ * The per-iteration exchange of the sharded k-means as ONE kernel per rank: reduce-scatter of the partial sums /
+ * counts by peer STORES into the row owner's inbox (+ one flag per row and sender), sums in rank order, centroid + norm
+ * (dd_kmeans_update's arithmetic) by the owner, all-gather of the fp32 centroid rows by peer stores, flag barrier.
+ * Replaces dd_comm_allreduce + dd_kmeans_update.
  * dd_peer_create allocates this rank's arena (bytes, zeroed) and returns its 64-byte cudaIpcMemHandle_t; the host
  * all-gathers the handles (world x 64 bytes, rank order) and passes them to dd_peer_connect.  The k-means buffers are
  * carved out of the arena at the same offsets (>= dd_peer_header_bytes()) on every rank: sum [R,D] f64 and cnt [R]
- * i64 hold the LOCAL partial results on entry; centroid [R,D] f32, cnorm [R] f32 and gcnt [R] i64 (global counts)
+ * i64 hold the LOCAL partial results on entry (dd_kmeans_lloyd with peer_ctx reads the pass's partial slots instead and
+ * leaves sum / cnt untouched); centroid [R,D] f32, cnorm [R] f32 and gcnt [R] i64 (global counts)
  * are written for all R = C*K rows on every rank.  Every rank must make the same sequence of exchange calls.
  * dd_peer_status: non-zero if a bounded flag wait timed out (synchronises the stream); a timed-out exchange reduces
  * nothing and stores nothing.  The bound is 10 s of wall time (DD_PEER_TIMEOUT_MS overrides it at dd_peer_create). */
@@ -200,11 +202,16 @@ int dd_peer_create(int rank, int world, size_t bytes, void** ctx, void* ipc_hand
 int dd_peer_connect(void* ctx, const void* all_handles);
 void* dd_peer_local(void* ctx);
 size_t dd_peer_header_bytes(void);
+/* bytes to request from dd_peer_create (on top of dd_peer_header_bytes()) for an R x D problem on `world` ranks: the five
+ * buffers above, each 256-byte aligned, plus the exchange kernel's inbox (one fp64 row + count per sender and owned row),
+ * which the library places at the tail of the arena.  Every rank must create its arena with the same size. */
+size_t dd_peer_arena_bytes(int R, int D, int world);
 int dd_peer_kmeans_exchange(void* ctx, size_t off_sum, size_t off_cnt, size_t off_centroid, size_t off_cnorm, size_t off_gcnt,
                             int R, int D, dd_stream_t stream);
 int dd_peer_status(void* ctx, dd_stream_t stream, int* status);
 /* Phase boundaries of the LAST exchange on this rank, microseconds since its kernel started (device %globaltimer):
- * us5 = {0, local slot reduce done, flag barrier A passed, owned rows reduced + stored, flag barrier B passed}.
+ * us5 = {0, CTA 0 pushed its rows to their owners, CTA 0's first owned row complete in the inbox, all owned rows
+ * updated + stored (last CTA), flag barrier B passed}.
  * Diagnostic (synchronises the stream); -1 for a phase that did not run (e.g. no slot reduction). */
 int dd_peer_timing(void* ctx, dd_stream_t stream, double* us5);
 /* `iters` Lloyd iterations launched back to back from C (no host round trip between them): per iteration

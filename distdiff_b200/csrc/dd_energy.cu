@@ -263,36 +263,55 @@ __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int tar
     __syncthreads();
 }
 
-// ONE launch: rank inside the class (warp-aggregated atomics) | grid barrier | exclusive scan of the class counts (every
-// CTA, in shared memory; CTA 0 also publishes off[] for the tile kernel) | scatter perm[off[c] + rank] = b.
-// grid <= 2 x #SMs CTAs of 256 threads (co-resident), grid-stride over the samples.
+// ONE launch: rank inside the class | grid barrier | exclusive scan of the class counts (every CTA, in shared memory; CTA 0
+// also publishes off[] for the tile kernel) | scatter perm[off[c] + rank] = b.
+// Rank, C + 2 <= CS_SMEM_OFF (the usual case): a shared-memory histogram per CTA (the atomic's return value is the sample's
+// rank inside the CTA), then ONE global atomic per (CTA, non-empty class) whose return value is the CTA's base inside the
+// class -- a single global round trip; the base stays in shared memory across the grid barrier.  Larger C: warp-aggregated
+// global atomics (match_any).  grid <= 2 x #SMs CTAs of 256 threads (co-resident), grid-stride over the samples.
 __global__ void __launch_bounds__(EN_THREADS)
 class_sort_kernel(const int64_t* __restrict__ target, int B, int C, int* __restrict__ counts /* [C+1], zero */,
                   int* __restrict__ rank /* [B] */, int* __restrict__ off /* [C+2] */, int* __restrict__ perm /* [B] */,
                   unsigned int* __restrict__ bar /* zero */) {
     __shared__ int soff[CS_SMEM_OFF];
+    __shared__ int sbase[CS_SMEM_OFF];   // per-CTA class histogram, then the CTA's base inside each class
     __shared__ int wsum[EN_THREADS / 32];
     const int lane = threadIdx.x & 31;
     const int stride = gridDim.x * EN_THREADS;
+    const int n = C + 1;
+    const bool in_smem = n + 1 <= CS_SMEM_OFF;
     pdl_launch_dependents();   // the tile kernel may be scheduled behind this grid (it waits for its completion before reading)
-    for (int b0 = blockIdx.x * EN_THREADS; b0 < B; b0 += stride) {
-        const int b = b0 + threadIdx.x;
-        const unsigned act = __ballot_sync(0xffffffffu, b < B);
-        if (b < B) {
+    if (in_smem) {
+        for (int i = threadIdx.x; i < n; i += EN_THREADS) sbase[i] = 0;
+        __syncthreads();
+        for (int b = blockIdx.x * EN_THREADS + threadIdx.x; b < B; b += stride) {
             const int64_t y = target[b];
             const int c = (y >= 0 && y < C) ? (int)y : C;
-            const unsigned m = __match_any_sync(act, c);
-            const int leader = __ffs(m) - 1;
-            int base = 0;
-            if (lane == leader) base = atomicAdd(counts + c, __popc(m));
-            base = __shfl_sync(m, base, leader);
-            rank[b] = base + __popc(m & ((1u << lane) - 1u));
+            rank[b] = atomicAdd(&sbase[c], 1);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += EN_THREADS) {
+            const int cnt = sbase[i];
+            sbase[i] = cnt > 0 ? atomicAdd(counts + i, cnt) : 0;
+        }
+    } else {
+        for (int b0 = blockIdx.x * EN_THREADS; b0 < B; b0 += stride) {
+            const int b = b0 + threadIdx.x;
+            const unsigned act = __ballot_sync(0xffffffffu, b < B);
+            if (b < B) {
+                const int64_t y = target[b];
+                const int c = (y >= 0 && y < C) ? (int)y : C;
+                const unsigned m = __match_any_sync(act, c);
+                const int leader = __ffs(m) - 1;
+                int base = 0;
+                if (lane == leader) base = atomicAdd(counts + c, __popc(m));
+                base = __shfl_sync(m, base, leader);
+                rank[b] = base + __popc(m & ((1u << lane) - 1u));
+            }
         }
     }
     grid_barrier(bar, gridDim.x);
     // exclusive scan of counts[0..C] -> offsets; thread t owns a contiguous chunk
-    const int n = C + 1;
-    const bool in_smem = n + 1 <= CS_SMEM_OFF;
     if (in_smem || blockIdx.x == 0) {
         const int per = (n + EN_THREADS - 1) / EN_THREADS;
         const int lo = threadIdx.x * per, hi = min(lo + per, n);
@@ -323,7 +342,7 @@ class_sort_kernel(const int64_t* __restrict__ target, int B, int C, int* __restr
         if (b < B) {
             const int64_t y = target[b];
             const int c = (y >= 0 && y < C) ? (int)y : C;
-            perm[(in_smem ? soff[c] : __ldcg(off + c)) + rank[b]] = b;
+            perm[(in_smem ? soff[c] + sbase[c] : __ldcg(off + c)) + rank[b]] = b;
         }
     }
 }
@@ -1327,9 +1346,10 @@ extern "C" int dd_energy_fwd_bwd(const float* f, const int64_t* target, const fl
     DD_REQUIRE(mode != 4 || pair_ok, DD_EUNSUPPORTED, "dd_energy_fwd_bwd: the warp-pair kernel needs both tables and K <= %d", dd::EP_MAXK);
     if (mode >= 2 || (mode == 0 && tile_ok && B >= dd::tile_min_b(K))) {
 #define ARGS f, target, g, l, B, D, C, K, gs, ls, normalize_f, score, per_sample, kstar, grad_f, (unsigned char*)ws, st
-        // warp-pair kernel (tables in shared memory, 16 rows per CTA in flight) from 64 samples per SM; below that the
-        // thread-group kernel's finer granularity (4 rows per CTA, 2 CTAs per SM for K <= 4) wins
-        if (mode == 4 || (mode != 3 && pair_ok && B >= 64 * dd::sm_count())) {
+        // warp-pair kernel (tables in shared memory, 16 rows per CTA in flight) for K >= 5 from 64 samples per SM.  Below that
+        // the thread-group kernel's finer granularity (4 rows per CTA) wins, and for K <= 4 it runs two CTAs per SM and is as
+        // fast as the pair kernel at any size (B = 65536, K = 3: 0.75 vs 0.73 of the HBM roofline; K = 10: 0.61 vs 0.70)
+        if (mode == 4 || (mode != 3 && pair_ok && K >= 5 && B >= 64 * dd::sm_count())) {
             if (K <= 4) return dd::launch_energy_pair<4>(ARGS);
             if (K <= 6) return dd::launch_energy_pair<6>(ARGS);
             if (K <= 8) return dd::launch_energy_pair<8>(ARGS);

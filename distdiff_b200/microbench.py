@@ -122,7 +122,7 @@ def run(want=lambda name: True, iters=10, ks=(3, 5, 10), latent_dtypes=(torch.fl
                 # the per-sample prototype reads, which are L2 hits (tables <= 8 MB) -- kept as survey_bytes only
                 nbytes = 2 * B * D * 4 + (K + 1) * min(B, C) * D * 4
                 for nf in (False, True):
-                    for mode in (("auto",) if B < 1024 else ("sample", "tile_cta", "tile_pair")):
+                    for mode in (("auto",) if B < 1024 else ("sample", "tile_cta", "tile_pair", "auto")):
                         t = timeit(lambda: ops.energy_fwd_bwd(f, y, g, l, 1.0, 1.0, nf, mode=mode), iters)
                         report(f"K4_energy_K{K}_B{B}_norm{int(nf)}_{mode}", nbytes, t, survey_bytes=B * (K + 3) * D * 4)
                     if want("eager") and K == 3:   # forward + autograd backward of generate_data.py:707-717 / :747-759

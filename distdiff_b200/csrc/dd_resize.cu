@@ -23,8 +23,11 @@
 // float4 per index; the generic path (strong up-scaling, MC > 4) walks a conservative candidate range.
 #include "dd_common.cuh"
 
+#include <cuda.h>   // CUtensorMap (types only: cuTensorMapEncodeTiled is fetched with cudaGetDriverEntryPoint, no -lcuda)
+
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 namespace dd {
@@ -288,6 +291,187 @@ bicubic_fwd_vec_kernel(const T* __restrict__ in, T* __restrict__ out, int Hin, i
     }
 }
 
+
+// -------------------------------------------------------------------------------------------------- forward, TMA staging
+// Same two passes, but the tile's input box arrives through ONE tensor-map copy (cp.async.bulk.tensor.3d over the
+// [planes][Hin][Win] view of the image, box = [1][rh_max][RW]): no staging loads, no index / clamp / predicate arithmetic
+// (39 % of the instructions of bicubic_fwd_vec_kernel), and the copy of a CTA overlaps the passes of its SM neighbours.
+// The box starts at the VIRTUAL coordinate of the first tap (it may be negative, or run past the image): the TMA unit
+// zero-fills what lies outside, and edge tiles then replicate the border row / column into those cells (ATen clamps the
+// tap index).  The box IS the staged region (RW = 4 * odd floats keeps pass 1's 16-byte row accesses conflict-free).
+// fp32 only: for 16-bit storage the box would land as raw 16-bit rows and need a conversion sweep into the fp32 region,
+// which measured slower (0.160 ms at B = 128) than converting while staging with plain loads (bicubic_fwd_vec_kernel, 0.152 ms).
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+
+template <typename T>
+__global__ void __launch_bounds__(RS_THREADS)
+bicubic_fwd_tma_kernel(const __grid_constant__ CUtensorMap tm, T* __restrict__ out, int Hin, int Win, int Hout, int Wout, float sy,
+                       float sx, int tiles_x, int tiles_y, int total_tiles, int S /* fp32 region row stride, 4 * odd */,
+                       int RWB /* box width (elements) */, int rh_max, int tp) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    static_assert(sizeof(T) == 4, "fp32 storage only");
+    constexpr int VN = Vec16<T>::N;
+    // One tile per CTA; the copies of a CTA's SM neighbours overlap its passes.  (A persistent variant with two boxes per CTA
+    // and the next tile's copy in flight was measured SLOWER, 0.128 vs 0.111 ms at B = 128 fp32: the kernel is bound by the
+    // issue slots of the two passes, and the second box costs a third of the resident warps.)
+    // box = region [rh_max][S] | tmpT [RS_TO][tp] | tap tables | mbarrier
+    const size_t box_bytes = ((size_t)rh_max * RWB * sizeof(T) + 127) / 128 * 128;
+    float* tmpT = reinterpret_cast<float*>(smraw + box_bytes);
+    float4* tx_c = reinterpret_cast<float4*>(tmpT + (((size_t)RS_TO * tp + 3) / 4 * 4));
+    float4* ty_c = tx_c + RS_TO;
+    int* tx_0 = reinterpret_cast<int*>(ty_c + RS_TO);
+    int* ty_0 = tx_0 + RS_TO;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(ty_0 + RS_TO);
+    const int tiles = tiles_x * tiles_y;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    auto tile_origin = [&](int t, int& plane, int& ox0, int& oy0) {
+        plane = t / tiles;
+        const int tile = t - plane * tiles;
+        const int tyi = tile / tiles_x;
+        ox0 = (tile - tyi * tiles_x) * RS_TO; oy0 = tyi * RS_TO;
+    };
+    // The innermost TMA coordinate must keep the global address 16-byte aligned (measured: tools/probes/tma_probe.cu -- a
+    // 4-byte-granular start is an illegal instruction, out-of-bounds starts are fine), hence the floor to VN elements
+    auto issue = [&](int t, int stage) {
+        int plane, ox0, oy0;
+        tile_origin(t, plane, ox0, oy0);
+        const int xa = floor_div(tap_floor(ox0, sx) - 1, VN) * VN, vy_lo = tap_floor(oy0, sy) - 1;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the box was written by threads (border cells) before
+        mbar_expect_tx(&bar[stage], (uint32_t)((size_t)rh_max * RWB * sizeof(T)));
+        tma_load_3d(smraw + stage * box_bytes, &tm, xa, vy_lo, plane, &bar[stage]);
+    };
+    if (tid == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_fence_init();
+        if ((int)blockIdx.x < total_tiles) issue(blockIdx.x, 0);
+    }
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+        constexpr int stage = 0;
+        int plane, ox0, oy0;
+        tile_origin(t, plane, ox0, oy0);
+        const int nx = min(RS_TO, Wout - ox0), ny = min(RS_TO, Hout - oy0);
+        const int vx_lo = tap_floor(ox0, sx) - 1, vy_lo = tap_floor(oy0, sy) - 1;    // virtual coordinate of the first tap
+        const int xa = floor_div(vx_lo, VN) * VN;                                     // staged column 0
+        const int vx_hi = tap_floor(ox0 + nx - 1, sx) + 2, rh = tap_floor(oy0 + ny - 1, sy) + 2 - vy_lo + 1;
+        if (tid >= 32 && tid < 32 + RS_TO) {                           // tap tables of the tile, while the box is in flight
+            const int l = tid - 32;
+            if (l < ny) {
+                const Taps tp_ = cubic_taps(oy0 + l, sy);
+                ty_c[l] = make_float4(tp_.c[0], tp_.c[1], tp_.c[2], tp_.c[3]);
+                ty_0[l] = tp_.f - 1 - vy_lo;
+            }
+        } else if (tid >= 64 && tid < 64 + RS_TO) {
+            const int l = tid - 64;
+            if (l < nx) {
+                const Taps tp_ = cubic_taps(ox0 + l, sx);
+                tx_c[l] = make_float4(tp_.c[0], tp_.c[1], tp_.c[2], tp_.c[3]);
+                tx_0[l] = tp_.f - 1 - xa;
+            }
+        }
+        __syncthreads();            // barriers initialised (first iteration) and tap tables written before anyone goes on
+        mbar_wait<20>(&bar[stage], it & 1);
+        float* region = reinterpret_cast<float*>(smraw + stage * box_bytes);
+        const bool edge_y = vy_lo < 0 || vy_lo + rh > Hin, edge_x = vx_lo < 0 || vx_hi >= Win;
+        if (edge_y) {               // replicate the first / last image row into the virtual rows outside (whole staged width)
+            const int r_first = -vy_lo, r_last = Hin - 1 - vy_lo;     // staged rows of image rows 0 and Hin - 1
+            const int n_top = vy_lo < 0 ? r_first : 0, n_bot = r_last < rh - 1 ? rh - 1 - r_last : 0;
+            for (int i = tid; i < (n_top + n_bot) * (S / 4); i += RS_THREADS) {
+                const int q = i / (S / 4), c4 = i - q * (S / 4);
+                const int ry = q < n_top ? q : r_last + 1 + (q - n_top);
+                reinterpret_cast<float4*>(region + ry * S)[c4] = reinterpret_cast<const float4*>(region + (q < n_top ? r_first : r_last) * S)[c4];
+            }
+            __syncthreads();
+        }
+        if (edge_x) {               // then the border columns (corners come out right: the rows are already replicated)
+            const int c_first = -xa, c_last = Win - 1 - xa;
+            for (int ry = tid; ry < rh; ry += RS_THREADS) {
+                float* drow = region + ry * S;
+                if (vx_lo < 0) {
+                    const float e = drow[c_first];
+                    for (int cx = 0; cx < c_first; ++cx) drow[cx] = e;
+                }
+                if (vx_hi >= Win) {
+                    const float e = drow[c_last];
+                    for (int cx = c_last + 1; cx <= vx_hi - xa; ++cx) drow[cx] = e;
+                }
+            }
+            __syncthreads();
+        }
+        {   // pass 1: cubic_interp1d along x of every staged row
+            constexpr int PW = RS_TO / (RS_THREADS / 32);                  // columns per warp
+#pragma unroll
+            for (int j = 0; j < PW; ++j) {
+                const int l = warp + j * (RS_THREADS / 32);
+                if (l >= nx) break;
+                const float4 c = tx_c[l];
+                const int x0 = tx_0[l];
+                const float* rcol = region + (x0 & ~3) + lane * S;
+                float* trow = tmpT + l * tp + lane;
+                const int nrow = rh - lane;
+                switch (x0 & 3) {                                          // warp-uniform: the row loop is specialised per shift
+                    case 0: interp_rows<0>(rcol, trow, nrow, S, c); break;
+                    case 1: interp_rows<1>(rcol, trow, nrow, S, c); break;
+                    case 2: interp_rows<2>(rcol, trow, nrow, S, c); break;
+                    default: interp_rows<3>(rcol, trow, nrow, S, c); break;
+                }
+            }
+        }
+        __syncthreads();
+        // pass 2: then along y (lanes along x, odd column stride)
+        if (lane < nx) {
+            T* dst = out + (int64_t)plane * Hout * Wout + (int64_t)oy0 * Wout + ox0 + lane;
+            const float* tcol = tmpT + lane * tp;
+            for (int ly = warp; ly < ny; ly += RS_THREADS / 32) {
+                const float4 cy = ty_c[ly];
+                const float* tq = tcol + ty_0[ly];
+                const float v = tq[0] * cy.x + tq[1] * cy.y + tq[2] * cy.z + tq[3] * cy.w;
+                dst[(int64_t)ly * Wout] = from_f32<T>(v);
+            }
+        }
+        __syncthreads();            // tmpT / the tap tables are rewritten by the next tile
+        if (tid == 0 && t + (int)gridDim.x < total_tiles) issue(t + gridDim.x, 0);   // (grids smaller than the tile count)
+    }
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (the library does not link libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+template <typename T> struct TmType;
+template <> struct TmType<float> { static constexpr CUtensorMapDataType v = CU_TENSOR_MAP_DATA_TYPE_FLOAT32; };
+template <> struct TmType<__half> { static constexpr CUtensorMapDataType v = CU_TENSOR_MAP_DATA_TYPE_FLOAT16; };
+template <> struct TmType<__nv_bfloat16> { static constexpr CUtensorMapDataType v = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16; };
+
+// [planes][H][W] view of a contiguous image batch, box [1][box_h][box_w]; false when the shape does not qualify
+template <typename T>
+static bool make_plane_map(CUtensorMap* tm, const void* base, int64_t planes, int H, int W, int box_w, int box_h) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc || !aligned16(base) || ((size_t)W * sizeof(T)) % 16 != 0 || box_w > 256 || box_h > 256 || (box_w * sizeof(T)) % 16 != 0) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)planes};
+    const cuuint64_t strides[2] = {(cuuint64_t)W * sizeof(T), (cuuint64_t)H * W * sizeof(T)};
+    const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    return enc(tm, TmType<T>::v, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // -------------------------------------------------------------------------------------------------- backward
 // range of output indices whose taps can touch input index i (conservative; the exact test is done per tap)
 __device__ __forceinline__ void out_range(int i, float scale, int n_out, int& lo, int& hi) {
@@ -421,27 +605,31 @@ __device__ __forceinline__ void store4(T* p, const float (&a)[4], bool vec, int 
     }
 }
 
-// smem: oc_x [gw_max] f4 | oc_y [gh_max] f4 | wx [RS_BX] f4 | wy [by] f4 | tmp [gh_max + MC][RS_BX] | gs [gh_max][GW] |
-//       of_x [gw_max] | of_y [gh_max] | lox [RS_BX] | loy [by]          (GW = gw_max + MC: zero columns behind every row)
+// smem: gs [gh_max][GW] | oc_x [gw_max] f4 | oc_y [gh_max] f4 | wx [RS_BX] f4 | wy [by] f4 | tmp [gh_max + MC][RS_BX] |
+//       of_x [gw_max] | of_y [gh_max] | lox [RS_BX] | loy [by] | mbarrier      (GW = gw_max + MC: zero columns behind every row)
 // Both passes give every thread 4 adjacent input columns: 16 threads cover a tile row, a warp two rows.
 // VEC (Wout % VN == 0, 16-byte aligned grad_out): the staged region starts at a 16-byte boundary of the row and is
 // filled with 16-byte loads / stores; GW is then a multiple of the vector width.
-template <typename T, int MC, bool VEC>
+// TMA (fp32, VEC): the upstream-gradient region arrives as ONE tensor-map box (zero-filled outside the image) while the
+// CTA builds its tap tables; columns past the region then hold real neighbours instead of zeros, which only ever meet
+// zero weights.
+template <typename T, int MC, bool VEC, bool TMA>
 __global__ void __launch_bounds__(RS_THREADS)
 bicubic_bwd_fast_kernel(const T* __restrict__ gout, T* __restrict__ gin, int Hin, int Win, int Hout, int Wout, float sy, float sx,
-                        int tiles_x, int tiles_y, int gw_max, int gh_max, int by, int vec_ok, int GW) {
-    extern __shared__ __align__(16) float sm[];
+                        int tiles_x, int tiles_y, int gw_max, int gh_max, int by, int vec_ok, int GW, const __grid_constant__ CUtensorMap tm) {
+    extern __shared__ __align__(128) float sm[];
     constexpr int VN = Vec16<T>::N;
-    float4* oc_x = reinterpret_cast<float4*>(sm);
+    float* gs = sm;                                                    // [gh_max][GW], 128-byte aligned (TMA destination)
+    float4* oc_x = reinterpret_cast<float4*>(gs + ((size_t)gh_max * GW + 31) / 32 * 32);
     float4* oc_y = oc_x + gw_max;
     float4* wx = oc_y + gh_max;
     float4* wy = wx + RS_BX;
     float* tmp = reinterpret_cast<float*>(wy + by);
-    float* gs = tmp + (size_t)(gh_max + MC) * RS_BX;
-    int* of_x = reinterpret_cast<int*>(gs + (size_t)gh_max * GW);
+    int* of_x = reinterpret_cast<int*>(tmp + (size_t)(gh_max + MC) * RS_BX);
     int* of_y = of_x + gw_max;
     int* lox = of_y + gh_max;
     int* loy = lox + RS_BX;
+    uint64_t* bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(loy + by) + 7) & ~(uintptr_t)7);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tiles = tiles_x * tiles_y;
     const int64_t plane = blockIdx.x / tiles;
@@ -455,7 +643,14 @@ bicubic_bwd_fast_kernel(const T* __restrict__ gout, T* __restrict__ gin, int Hin
     if (VEC) ox_lo = (ox_lo / VN) * VN;
     const int gw = ox_hi - ox_lo + 1, gh = oy_hi - oy_lo + 1;
     const T* g = gout + plane * (int64_t)Hout * Wout + (int64_t)oy_lo * Wout + ox_lo;
-    if (VEC) {   // 16-byte vectors; whole vectors past the region / the image row are zeros
+    if (TMA) {
+        if (tid == 0) {
+            mbar_init(bar, 1);
+            mbar_fence_init();
+            mbar_expect_tx(bar, (uint32_t)((size_t)gh_max * GW * sizeof(T)));
+            tma_load_3d(gs, &tm, ox_lo, oy_lo, (int)plane, bar);
+        }
+    } else if (VEC) {   // 16-byte vectors; whole vectors past the region / the image row are zeros
         constexpr int UN = sizeof(T) == 4 ? 4 : 2;
         const int nvr = GW / VN;
         const float inv = 1.0f / (float)nvr;
@@ -518,6 +713,7 @@ bicubic_bwd_fast_kernel(const T* __restrict__ gout, T* __restrict__ gin, int Hin
     constexpr int QPR = RS_BX / 4;                 // threads per tile row
     constexpr int RPI = RS_THREADS / QPR;          // rows per iteration
     const int q = tid % QPR, rgrp = tid / QPR;
+    if (TMA) mbar_wait<20>(bar, 0);                // the box has landed (the barrier was initialised before the CTA barriers above)
     {   // horizontal pass: tmp[ry][ix] = sum_m gs[ry][lox[ix] + m] * wx[ix][m]
         float w[4][4];
         int l0[4];
@@ -593,6 +789,21 @@ static int launch_fwd(const void* in, void* out, int64_t planes, int Hin, int Wi
     const int tiles_x = (Wout + RS_TO - 1) / RS_TO, tiles_y = (Hout + RS_TO - 1) / RS_TO;
     const int64_t blocks = planes * tiles_x * tiles_y;
     DD_REQUIRE(blocks < (1ll << 31), DD_EUNSUPPORTED, "dd_bicubic_resize_fwd: too many tiles");
+    if constexpr (sizeof(T) == 4) {
+        if (!getenv("DD_K8_NO_TMA")) {   // tensor-map staging (DD_K8_NO_TMA: development switch back to the load/store staging below)
+            const int S = (((rw + (VN - 1) + 4 + 3) / 4) | 1) * 4;  // alignment slack + span + the second float4 of the last tap, 4 * odd
+            const size_t box_bytes = ((size_t)rh * S * sizeof(T) + 127) / 128 * 128;
+            const size_t smem = box_bytes + (((size_t)RS_TO * tp + 3) / 4 * 4 + RS_TO * 10) * sizeof(float) + 16;
+            CUtensorMap tm;
+            if (smem <= 100 * 1024 && make_plane_map<T>(&tm, in, planes, Hin, Win, S, rh)) {
+                auto kern = bicubic_fwd_tma_kernel<T>;
+                DD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                kern<<<(unsigned)blocks, RS_THREADS, smem, st>>>(tm, (T*)out, Hin, Win, Hout, Wout, sy, sx, tiles_x, tiles_y, (int)blocks, S, S, rh, tp);
+                DD_LAUNCH_OK();
+                return 0;
+            }
+        }
+    }
     if ((Win % VN == 0) && aligned16(in)) {
         const int S = (((rw + 2 * VN + 4 + 3) / 4) | 1) * 4;   // + alignment slack on both sides + the second float4 of the last tap
         const size_t smem = ((size_t)S * rh + (size_t)RS_TO * tp + RS_TO * 10) * sizeof(float);
@@ -629,7 +840,7 @@ static int launch_bwd_fast(const void* gout, void* gin, int64_t planes, int Hin,
     size_t smem = 0;
     for (; by >= 8; by /= 2) {
         gh_max = out_span(by, sy);
-        smem = ((size_t)(gw_max + gh_max + RS_BX + by) * 5 + (size_t)gh_max * GW + (size_t)(gh_max + MC) * RS_BX) * sizeof(float);
+        smem = ((size_t)(gw_max + gh_max + RS_BX + by) * 5 + ((size_t)gh_max * GW + 31) / 32 * 32 + (size_t)(gh_max + MC) * RS_BX + 4) * sizeof(float) + 16;
         if (smem <= 56 * 1024) break;
     }
     done = false;
@@ -637,11 +848,15 @@ static int launch_bwd_fast(const void* gout, void* gin, int64_t planes, int Hin,
     const int tiles_x = (Win + RS_BX - 1) / RS_BX, tiles_y = (Hin + by - 1) / by;
     const int64_t blocks = planes * tiles_x * tiles_y;
     DD_REQUIRE(blocks < (1ll << 31), DD_EUNSUPPORTED, "dd_bicubic_resize_bwd: too many tiles");
-    auto kern = vec ? bicubic_bwd_fast_kernel<T, MC, true> : bicubic_bwd_fast_kernel<T, MC, false>;
+    CUtensorMap tm = {};
+    bool tma = false;
+    if constexpr (sizeof(T) == 4) tma = vec && !getenv("DD_K8_NO_TMA") && make_plane_map<T>(&tm, gout, planes, Hout, Wout, GW, gh_max);
+    auto kern = tma ? bicubic_bwd_fast_kernel<T, MC, true, sizeof(T) == 4>
+                    : (vec ? bicubic_bwd_fast_kernel<T, MC, true, false> : bicubic_bwd_fast_kernel<T, MC, false, false>);
     DD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int vec_ok = (Win % 4 == 0) && aligned16(gin);   // 4-column stores: 16 B (fp32) / 8 B (16-bit) aligned
     kern<<<(unsigned)blocks, RS_THREADS, smem, st>>>((const T*)gout, (T*)gin, Hin, Win, Hout, Wout, sy, sx, tiles_x, tiles_y, gw_max, gh_max, by,
-                                                    vec_ok, GW);
+                                                    vec_ok, GW, tm);
     DD_LAUNCH_OK();
     done = true;
     return 0;

@@ -311,7 +311,7 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* t
 template <typename T>
 __global__ void __launch_bounds__(RS_THREADS)
 bicubic_fwd_tma_kernel(const __grid_constant__ CUtensorMap tm, T* __restrict__ out, int Hin, int Win, int Hout, int Wout, float sy,
-                       float sx, int tiles_x, int tiles_y, int total_tiles, int S /* fp32 region row stride, 4 * odd */,
+                       float sx, int S /* fp32 region row stride, 4 * odd */,
                        int RWB /* box width (elements) */, int rh_max, int tp) {
     extern __shared__ __align__(128) unsigned char smraw[];
     static_assert(sizeof(T) == 4, "fp32 storage only");
@@ -327,38 +327,22 @@ bicubic_fwd_tma_kernel(const __grid_constant__ CUtensorMap tm, T* __restrict__ o
     int* tx_0 = reinterpret_cast<int*>(ty_c + RS_TO);
     int* ty_0 = tx_0 + RS_TO;
     uint64_t* bar = reinterpret_cast<uint64_t*>(ty_0 + RS_TO);
-    const int tiles = tiles_x * tiles_y;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    auto tile_origin = [&](int t, int& plane, int& ox0, int& oy0) {
-        plane = t / tiles;
-        const int tile = t - plane * tiles;
-        const int tyi = tile / tiles_x;
-        ox0 = (tile - tyi * tiles_x) * RS_TO; oy0 = tyi * RS_TO;
-    };
-    // The innermost TMA coordinate must keep the global address 16-byte aligned (measured: tools/probes/tma_probe.cu -- a
-    // 4-byte-granular start is an illegal instruction, out-of-bounds starts are fine), hence the floor to VN elements
-    auto issue = [&](int t, int stage) {
-        int plane, ox0, oy0;
-        tile_origin(t, plane, ox0, oy0);
-        const int xa = floor_div(tap_floor(ox0, sx) - 1, VN) * VN, vy_lo = tap_floor(oy0, sy) - 1;
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the box was written by threads (border cells) before
-        mbar_expect_tx(&bar[stage], (uint32_t)((size_t)rh_max * RWB * sizeof(T)));
-        tma_load_3d(smraw + stage * box_bytes, &tm, xa, vy_lo, plane, &bar[stage]);
-    };
-    if (tid == 0) {
-        mbar_init(&bar[0], 1);
-        mbar_fence_init();
-        if ((int)blockIdx.x < total_tiles) issue(blockIdx.x, 0);
-    }
-    uint32_t it = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-        constexpr int stage = 0;
-        int plane, ox0, oy0;
-        tile_origin(t, plane, ox0, oy0);
+    // grid = (tiles_x, tiles_y, planes): no index arithmetic to find the tile
+    const int plane = blockIdx.z, ox0 = blockIdx.x * RS_TO, oy0 = blockIdx.y * RS_TO;
+    {
         const int nx = min(RS_TO, Wout - ox0), ny = min(RS_TO, Hout - oy0);
         const int vx_lo = tap_floor(ox0, sx) - 1, vy_lo = tap_floor(oy0, sy) - 1;    // virtual coordinate of the first tap
         const int xa = floor_div(vx_lo, VN) * VN;                                     // staged column 0
         const int vx_hi = tap_floor(ox0 + nx - 1, sx) + 2, rh = tap_floor(oy0 + ny - 1, sy) + 2 - vy_lo + 1;
+        // The innermost TMA coordinate must keep the global address 16-byte aligned (measured: tools/probes/tma_probe.cu -- a
+        // 4-byte-granular start is an illegal instruction, out-of-bounds starts are fine), hence xa = floor to VN elements
+        if (tid == 0) {
+            mbar_init(&bar[0], 1);
+            mbar_fence_init();
+            mbar_expect_tx(&bar[0], (uint32_t)((size_t)rh_max * RWB * sizeof(T)));
+            tma_load_3d(smraw, &tm, xa, vy_lo, plane, &bar[0]);
+        }
         if (tid >= 32 && tid < 32 + RS_TO) {                           // tap tables of the tile, while the box is in flight
             const int l = tid - 32;
             if (l < ny) {
@@ -375,8 +359,8 @@ bicubic_fwd_tma_kernel(const __grid_constant__ CUtensorMap tm, T* __restrict__ o
             }
         }
         __syncthreads();            // barriers initialised (first iteration) and tap tables written before anyone goes on
-        mbar_wait<20>(&bar[stage], it & 1);
-        float* region = reinterpret_cast<float*>(smraw + stage * box_bytes);
+        mbar_wait<20>(&bar[0], 0);
+        float* region = reinterpret_cast<float*>(smraw);
         const bool edge_y = vy_lo < 0 || vy_lo + rh > Hin, edge_x = vx_lo < 0 || vx_hi >= Win;
         if (edge_y) {               // replicate the first / last image row into the virtual rows outside (whole staged width)
             const int r_first = -vy_lo, r_last = Hin - 1 - vy_lo;     // staged rows of image rows 0 and Hin - 1
@@ -434,8 +418,6 @@ bicubic_fwd_tma_kernel(const __grid_constant__ CUtensorMap tm, T* __restrict__ o
                 dst[(int64_t)ly * Wout] = from_f32<T>(v);
             }
         }
-        __syncthreads();            // tmpT / the tap tables are rewritten by the next tile
-        if (tid == 0 && t + (int)gridDim.x < total_tiles) issue(t + gridDim.x, 0);   // (grids smaller than the tile count)
     }
 }
 
@@ -631,11 +613,17 @@ bicubic_bwd_fast_kernel(const T* __restrict__ gout, T* __restrict__ gin, int Hin
     int* loy = lox + RS_BX;
     uint64_t* bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(loy + by) + 7) & ~(uintptr_t)7);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int tiles = tiles_x * tiles_y;
-    const int64_t plane = blockIdx.x / tiles;
-    const int tile = blockIdx.x - (int)plane * tiles;
-    const int tyi = tile / tiles_x;
-    const int ix0 = (tile - tyi * tiles_x) * RS_BX, iy0 = tyi * by;
+    int64_t plane;
+    int ix0, iy0;
+    if (TMA) {   // grid = (tiles_x, tiles_y, planes)
+        plane = blockIdx.z; ix0 = blockIdx.x * RS_BX; iy0 = blockIdx.y * by;
+    } else {
+        const int tiles = tiles_x * tiles_y;
+        plane = blockIdx.x / tiles;
+        const int tile = blockIdx.x - (int)plane * tiles;
+        const int tyi = tile / tiles_x;
+        ix0 = (tile - tyi * tiles_x) * RS_BX; iy0 = tyi * by;
+    }
     const int ix1 = min(ix0 + RS_BX, Win), iy1 = min(iy0 + by, Hin);
     int ox_lo, ox_hi, oy_lo, oy_hi, t0, t1;
     out_range(ix0, sx, Wout, ox_lo, t1); out_range(ix1 - 1, sx, Wout, t0, ox_hi);
@@ -795,10 +783,10 @@ static int launch_fwd(const void* in, void* out, int64_t planes, int Hin, int Wi
             const size_t box_bytes = ((size_t)rh * S * sizeof(T) + 127) / 128 * 128;
             const size_t smem = box_bytes + (((size_t)RS_TO * tp + 3) / 4 * 4 + RS_TO * 10) * sizeof(float) + 16;
             CUtensorMap tm;
-            if (smem <= 100 * 1024 && make_plane_map<T>(&tm, in, planes, Hin, Win, S, rh)) {
+            if (smem <= 100 * 1024 && planes <= 65535 && tiles_y <= 65535 && make_plane_map<T>(&tm, in, planes, Hin, Win, S, rh)) {
                 auto kern = bicubic_fwd_tma_kernel<T>;
                 DD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                kern<<<(unsigned)blocks, RS_THREADS, smem, st>>>(tm, (T*)out, Hin, Win, Hout, Wout, sy, sx, tiles_x, tiles_y, (int)blocks, S, S, rh, tp);
+                kern<<<dim3(tiles_x, tiles_y, (unsigned)planes), RS_THREADS, smem, st>>>(tm, (T*)out, Hin, Win, Hout, Wout, sy, sx, S, S, rh, tp);
                 DD_LAUNCH_OK();
                 return 0;
             }
@@ -850,13 +838,14 @@ static int launch_bwd_fast(const void* gout, void* gin, int64_t planes, int Hin,
     DD_REQUIRE(blocks < (1ll << 31), DD_EUNSUPPORTED, "dd_bicubic_resize_bwd: too many tiles");
     CUtensorMap tm = {};
     bool tma = false;
-    if constexpr (sizeof(T) == 4) tma = vec && !getenv("DD_K8_NO_TMA") && make_plane_map<T>(&tm, gout, planes, Hout, Wout, GW, gh_max);
+    if constexpr (sizeof(T) == 4)
+        tma = vec && planes <= 65535 && tiles_y <= 65535 && !getenv("DD_K8_NO_TMA") && make_plane_map<T>(&tm, gout, planes, Hout, Wout, GW, gh_max);
     auto kern = tma ? bicubic_bwd_fast_kernel<T, MC, true, sizeof(T) == 4>
                     : (vec ? bicubic_bwd_fast_kernel<T, MC, true, false> : bicubic_bwd_fast_kernel<T, MC, false, false>);
     DD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int vec_ok = (Win % 4 == 0) && aligned16(gin);   // 4-column stores: 16 B (fp32) / 8 B (16-bit) aligned
-    kern<<<(unsigned)blocks, RS_THREADS, smem, st>>>((const T*)gout, (T*)gin, Hin, Win, Hout, Wout, sy, sx, tiles_x, tiles_y, gw_max, gh_max, by,
-                                                    vec_ok, GW, tm);
+    const dim3 grid = tma ? dim3(tiles_x, tiles_y, (unsigned)planes) : dim3((unsigned)blocks);
+    kern<<<grid, RS_THREADS, smem, st>>>((const T*)gout, (T*)gin, Hin, Win, Hout, Wout, sy, sx, tiles_x, tiles_y, gw_max, gh_max, by, vec_ok, GW, tm);
     DD_LAUNCH_OK();
     done = true;
     return 0;

@@ -340,6 +340,9 @@ bicubic_fwd_tma_kernel(const __grid_constant__ CUtensorMap tm, T* __restrict__ o
         if (tid == 0) {
             mbar_init(&bar[0], 1);
             mbar_fence_init();
+        }
+        __syncthreads();   // (racecheck: the barrier word is initialised before any mbarrier operation on it, also for thread 0 itself)
+        if (tid == 0) {
             mbar_expect_tx(&bar[0], (uint32_t)((size_t)rh_max * RWB * sizeof(T)));
             tma_load_3d(smraw, &tm, xa, vy_lo, plane, &bar[0]);
         }
@@ -635,6 +638,9 @@ bicubic_bwd_fast_kernel(const T* __restrict__ gout, T* __restrict__ gin, int Hin
         if (tid == 0) {
             mbar_init(bar, 1);
             mbar_fence_init();
+        }
+        __syncthreads();   // (racecheck: initialised before any mbarrier operation on it)
+        if (tid == 0) {
             mbar_expect_tx(bar, (uint32_t)((size_t)gh_max * GW * sizeof(T)));
             tma_load_3d(gs, &tm, ox_lo, oy_lo, (int)plane, bar);
         }

@@ -100,7 +100,10 @@ __device__ __forceinline__ bool wait_all(const uint32_t* flags, int stride, int 
     return __syncthreads_and(ok) != 0;
 }
 
-__global__ void __launch_bounds__(PEER_THREADS, 2)
+#ifndef DD_PEER_CTAS_PER_SM
+#define DD_PEER_CTAS_PER_SM 2
+#endif
+__global__ void __launch_bounds__(PEER_THREADS, DD_PEER_CTAS_PER_SM)
 kmeans_exchange_kernel(unsigned char* me, int rank, int world, uint32_t epoch, size_t off_sum, size_t off_cnt, size_t off_cen,
                        size_t off_cn, size_t off_gcnt, size_t off_inbox, size_t off_inbox_cnt, int rows_max, int R, int D,
                        unsigned long long timeout_ns, const float* __restrict__ ws_sum /* null: the local sums are final */,
@@ -269,11 +272,12 @@ kmeans_exchange_kernel(unsigned char* me, int rank, int world, uint32_t epoch, s
         double s[SLOT_NC];
 #pragma unroll
         for (int j = 0; j < SLOT_NC; ++j) s[j] = 0.0;
-        // the loads of 4 senders are issued before their ordered adds (local L2 / HBM: the rows were pushed here)
-        for (int p0 = 0; p0 < world; p0 += 4) {
-            double v[4][SLOT_NC];
+        // the loads of PS senders are issued before their ordered adds (local L2 / HBM: the rows were pushed here)
+        constexpr int PS = 4;
+        for (int p0 = 0; p0 < world; p0 += PS) {
+            double v[PS][SLOT_NC];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < PS; ++i) {
                 const int p = p0 + i < world ? p0 + i : world - 1;
                 const double* src = inbox + ((size_t)p * rows_max + rl) * D;
 #pragma unroll
@@ -283,7 +287,7 @@ kmeans_exchange_kernel(unsigned char* me, int rank, int world, uint32_t epoch, s
                 }
             }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < PS; ++i) {
                 if (p0 + i < world) {
 #pragma unroll
                     for (int j = 0; j < SLOT_NC; ++j) s[j] += v[i][j];   // rank order

@@ -22,7 +22,9 @@ def main(path, out):
         name = k.split("(")[0]
         by[name][0] += 1
         by[name][1] += t
-    ours = [(i, k, t) for i, k, t in rows if "dd::" in k]
+    OURS = ("dd::", "kmeans_", "rownorm_", "class_mean", "partial_reduce", "energy_", "class_sort", "cfg_ddim", "affine_", "add_noise",
+            "bicubic_", "image_to_uint8", "agglo_", "normalize_rows")   # ncu prints some names without the namespace
+    ours = [(i, k, t) for i, k, t in rows if any(o in k for o in OURS)]
     t_ours = sum(t for _, _, t in ours)
     with open(out, "w") as f:
         f.write(f"# ncu launch list summary ({path})\n\n")

@@ -307,6 +307,58 @@ def extract_prototype(args, train_loader, model, coll: Optional[Collective] = No
     return g.cpu().numpy(), l.cpu().numpy()
 
 
+class GpuDecodeLoader:
+    """Opt-in (``--gpu_decode``) replacement of the PIL decode + ``Resize((224, 224))`` + ``ToTensor`` + ``Normalize`` loader of
+    dataloader.py:736-743: JPEG files are read as bytes, decoded by nvJPEG on the GPU
+    (``torchvision.io.decode_jpeg(device=cuda)``, EXIF orientation applied), resized there (bilinear with antialiasing, the
+    result rounded to the uint8 grid like PIL's) and normalised -- the guide features never touch the host.  Files nvJPEG
+    does not take (PNG, CMYK, corrupt headers) go through the reference's PIL path, image by image.
+    NOT bit-identical to the PIL path: nvJPEG's IDCT and the float resize differ from libjpeg / PIL's fixed-point resize by
+    +-1-2 grey levels per pixel; class-mean prototypes agree to 5e-3 relative (tests/test_gpu_generate.py::test_gpu_decode_matches_pil_path).
+    The default stays the reference's loader."""
+
+    def __init__(self, paths, targets, device, batch_size=64, fallback=None, fallback_index=None, transform=None):
+        self.paths, self.targets, self.device, self.bs = list(paths), list(targets), device, batch_size
+        self.fallback, self.fallback_index, self.transform = fallback, fallback_index, transform
+        self.mean = torch.tensor([0.485, 0.456, 0.406], device=device).view(1, 3, 1, 1)
+        self.std = torch.tensor([0.229, 0.224, 0.225], device=device).view(1, 3, 1, 1)
+        self.decoded_on_gpu = 0
+
+    def __len__(self):
+        return (len(self.paths) + self.bs - 1) // self.bs
+
+    def _pil(self, j):
+        img = self.fallback.image(self.fallback_index[j])
+        return self.transform(img).to(self.device)
+
+    def __iter__(self):
+        from torchvision.io import ImageReadMode, decode_jpeg, read_file
+        for b0 in range(0, len(self.paths), self.bs):
+            js = list(range(b0, min(b0 + self.bs, len(self.paths))))
+            raw, jpeg = [], []
+            for j in js:
+                data = read_file(self.paths[j])
+                ok = data.numel() > 3 and int(data[0]) == 0xFF and int(data[1]) == 0xD8          # JPEG SOI marker
+                raw.append(data); jpeg.append(ok)
+            out = [None] * len(js)
+            todo = [i for i, ok in enumerate(jpeg) if ok]
+            if todo:
+                try:
+                    imgs = decode_jpeg([raw[i] for i in todo], mode=ImageReadMode.RGB, device=self.device, apply_exif_orientation=True)
+                except RuntimeError:
+                    imgs, todo = [], []
+                for i, im in zip(todo, imgs):
+                    x = torch.nn.functional.interpolate(im[None].float(), size=(224, 224), mode="bilinear", antialias=True,
+                                                        align_corners=False)
+                    x = x.round_().clamp_(0, 255) / 255.0                              # PIL resizes on the uint8 grid
+                    out[i] = ((x - self.mean) / self.std)[0]
+                    self.decoded_on_gpu += 1
+            for i, j in enumerate(js):
+                if out[i] is None:
+                    out[i] = self._pil(j)
+            yield torch.stack(out, 0), torch.tensor([self.targets[j] for j in js])
+
+
 def prototype_path(args) -> str:
     """dataloader.py:725-727 (commented out upstream)."""
     save_dir = "./save/prototypes/{}/{}/".format(args.arch, args.dataset)
@@ -337,7 +389,8 @@ def prototype_cache_key(args, model) -> str:
             "dataset": getattr(args, "dataset", None), "data_root": os.path.abspath(getattr(args, "data_root", "data")),
             "synthetic": [getattr(args, "synthetic_classes", None), getattr(args, "synthetic_per_class", None)],
             "seed": getattr(args, "seed", None), "tiny": bool(getattr(args, "tiny_models", False)),
-            "cluster_method": getattr(args, "cluster_method", "agglomerative"), "K": int(args.K)}
+            "cluster_method": getattr(args, "cluster_method", "agglomerative"), "K": int(args.K),
+            "gpu_decode": bool(getattr(args, "gpu_decode", False))}
     return json.dumps(meta, sort_keys=True)
 
 
@@ -380,6 +433,12 @@ def extract_prototypes_with_encoder(args, model, trainset_factory: Optional[Call
         idx = list(range(min(per * coll.rank, n), min(per * (coll.rank + 1), n)))
         trainset = tdata.Subset(trainset, idx)
     loader = tdata.DataLoader(trainset, batch_size=64, shuffle=False, drop_last=False)
+    if getattr(args, "gpu_decode", False):
+        base = trainset.dataset if isinstance(trainset, tdata.Subset) else trainset
+        idx = list(trainset.indices) if isinstance(trainset, tdata.Subset) else list(range(len(base)))
+        if hasattr(base, "paths") and idx and all(os.path.isfile(base.paths[i]) for i in idx[:4]):
+            loader = GpuDecodeLoader([base.paths[i] for i in idx], [base.targets[i] for i in idx],
+                                     next(model.parameters()).device, fallback=base, fallback_index=idx, transform=transform)
     model = model.float()
     g, l = extract_prototype(args, loader, model, coll)
     if cache and method == "agglomerative" and (coll is None or coll.rank == 0):

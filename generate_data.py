@@ -72,6 +72,8 @@ def parse_args(input_args=None):
     p.add_argument("--cuda_graph", action="store_true", help="replay the unguided step (UNet + K5) from a CUDA graph")
     p.add_argument("--cache_latents", action="store_true", help="persist save/vae_embedding/.../image_latents.pt like the reference")
     p.add_argument("--shard_latents", action="store_true", help="(default behaviour now; kept for compatibility)")
+    p.add_argument("--gpu_decode", action="store_true",
+                   help="prototype stage: decode + resize the train JPEGs on the GPU (nvJPEG) instead of PIL; prototypes ~5e-3 from the PIL path")
     p.add_argument("--tiny_models", action="store_true", help="tiny random-init UNet/VAE/guide (tests)")
     p.add_argument("--max_batches", type=int, default=None, help="stop after this many batches (smoke runs)")
     args, unknown = p.parse_known_args(input_args)

@@ -27,6 +27,16 @@ def test_header_symbols_exported_and_bound():
     assert handle.dd_abi_version() == 1
     assert handle.dd_proto_workspace_bytes(2048, 100, 3) > 0
     assert handle.dd_agglo_workspace_bytes(30, 100) >= 100 * 30 * 30 * 8
+    # peer arena: five exchanged buffers + the exchange kernel's inbox (one fp64 row + count per sender and owned row)
+    hdr = handle.dd_peer_header_bytes()
+    assert hdr >= 1024 + 4 * 65536 and hdr % 256 == 0                      # flag rows / status / stamps + one inbox flag per row
+    for R, D, P in ((300, 2048, 8), (1000, 2048, 8), (301, 512, 3), (7, 64, 1)):
+        rows_max = -(-R // P)
+        need = handle.dd_peer_arena_bytes(R, D, P)
+        assert need >= R * (D * 12 + 20) + P * rows_max * (D * 8 + 8)
+        assert need <= R * (D * 12 + 20) + P * rows_max * (D * 8 + 8) + 16 * 256
+    assert handle.dd_peer_arena_bytes(0, 2048, 8) == 0
+    assert handle.dd_energy_workspace_bytes(65536, 100) >= 2 * 65536 * 4 + 102 * 8
 
 
 def test_no_cpu_fallback():

@@ -272,6 +272,22 @@ def test_energy_tile_matches_sample_kernel(ops, cuda_device, K):
             assert (a[3] - b[3]).norm() <= 2e-6 * a[3].norm()
 
 
+@pytest.mark.parametrize("C", [1000, 5000])
+def test_energy_class_bucketing_many_classes(ops, cuda_device, C):
+    """The class bucketing of the large-batch kernels: shared-memory histogram (C + 2 <= 4096) and the warp-aggregated global
+    atomics beyond that; both large-batch kernels must agree with the per-sample kernel when most class runs hold 1-5 samples."""
+    B, K, D = 20000, 3, 512
+    f, gp, lp, y = _energy_case(B, C, K, D, 900 + C)
+    args = (f.to(cuda_device), y, gp.to(cuda_device), lp.to(cuda_device), 1.0, 1.0, True)
+    a = ops.energy_fwd_bwd(*args, mode="sample")
+    for mode in ("tile_cta", "tile_pair"):
+        b = ops.energy_fwd_bwd(*args, mode=mode)
+        assert abs(float(a[0]) - float(b[0])) <= 2e-6 * abs(float(a[0]))
+        assert torch.allclose(a[1], b[1], rtol=2e-6, atol=1e-7)
+        assert (a[2] != b[2]).float().mean() < 1e-3
+        assert (a[3] - b[3]).norm() <= 2e-6 * a[3].norm()
+
+
 @pytest.mark.parametrize("mode", ["tile_pair", "tile_cta"])
 @pytest.mark.parametrize("normalize_f", [False, True])
 def test_energy_tile_small_distances_take_the_exact_pass(ops, cuda_device, normalize_f, mode):
@@ -557,6 +573,21 @@ def test_bicubic_resize_bwd(ops, cuda_device, shape, size):
     assert np.abs(got.cpu().numpy() - ref).max() <= 1e-5 * np.abs(ref).max()
     again = ops.bicubic_resize_bwd(g.to(cuda_device), shape[2:])
     assert torch.equal(got, again)                              # gather, fixed order: bit-reproducible
+
+
+def test_bicubic_tma_staging_matches_plain_staging(ops, cuda_device, monkeypatch):
+    """fp32 forward / backward: the tensor-map (TMA) staged kernels and the load/store staged ones they replace give the same
+    bits (same two passes, same order), edge tiles included; DD_K8_NO_TMA is the library's development switch."""
+    x = torch.randn(3, 3, 512, 512, generator=_g(31)).to(cuda_device)
+    g = torch.randn(3, 3, 224, 224, generator=_g(32)).to(cuda_device)
+    small = torch.randn(2, 1, 64, 48, generator=_g(33)).to(cuda_device)
+    outs = []
+    for no_tma in ("", "1"):
+        if no_tma:
+            monkeypatch.setenv("DD_K8_NO_TMA", no_tma)
+        outs.append((ops.bicubic_resize(x, (224, 224)), ops.bicubic_resize_bwd(g, (512, 512)), ops.bicubic_resize(small, (20, 30))))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
 
 
 def test_bicubic_resize_autograd(ops, cuda_device):

@@ -163,6 +163,8 @@ def test_gpu_decode_matches_pil_path(cuda_device, tmp_path, monkeypatch):
             img.save(d / f"image_{i:04d}.jpg", quality=92)
     torch.manual_seed(0)
     model = nets.create_model("resnet18", num_classes=5).to(cuda_device).eval()
+    with torch.no_grad():
+        model.encode_image(torch.zeros(64, 3, 224, 224, device=cuda_device))       # cuDNN warm-up outside the timed loaders
     res = {}
     for gpu in (False, True):
         args = types.SimpleNamespace(dataset="caltech-101", data_root=str(tmp_path / "data"), arch="resnet18", K=2,

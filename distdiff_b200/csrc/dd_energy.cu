@@ -7,17 +7,21 @@
 // hop when a whole CTA works on a sample), picks k* = argmax <f, l_k> (first max on ties), and writes
 // d score / d f_b.  The batch mean is finished deterministically by the last CTA to arrive (ticket).
 //
-// Two kernels:
-//   * energy_kernel: one CTA per sample (the reference's B = 1..16 and everything up to a few thousand samples,
-//     where latency matters): prototypes come straight from L2.
-//   * energy_tile_kernel (large B): the prototype reads of the per-sample kernel are (K+3) rows of L2->SM traffic
-//     per sample against 2 rows of HBM traffic, i.e. L2-bound at ~0.25-0.36 of the HBM roofline.  The tile kernel
-//     removes them: samples are bucketed by class (a counting sort in one small kernel), persistent CTAs walk
-//     contiguous runs of the class-sorted order, every thread OWNS 8 columns of D and keeps the class's K+1
-//     prototype slices in registers across the run, sample rows are gathered by the TMA engine (one
-//     cp.async.bulk per row through the permutation) into a shared-memory ring, and the per-sample sums
-//     (K dots [+ |f|^2], then 4 distance / Jacobian sums) are reduced by transposed warp shuffles + one
-//     shared-memory hop.  Per sample the SM then moves f once from HBM and grad once to HBM and nothing else.
+// Three kernels behind dd_energy_fwd_bwd (`mode`):
+//   * energy_kernel: one CTA per sample (the reference's B = 1..16 and everything up to ~1k samples, where latency
+//     matters): prototypes come straight from L2.
+//   * energy_tile_kernel (class-tiled, thread groups): the prototype reads of the per-sample kernel are (K+3) rows of L2->SM
+//     traffic per sample against 2 rows of HBM traffic, i.e. L2-bound at ~0.25-0.36 of the HBM roofline.  The tile kernels
+//     remove them: samples are bucketed by class (a counting sort in one small kernel), persistent CTAs walk contiguous runs
+//     of the class-sorted order, every thread OWNS 8 columns of D and keeps the class's K+1 prototype slices in registers
+//     across the run, sample rows are gathered by the TMA engine (one cp.async.bulk per row through the permutation) into a
+//     shared-memory ring, and the per-sample sums are reduced by a warp transposition + one shared-memory hop.  Any K <= 16,
+//     either table may be missing; 2 CTAs per SM for K <= 4 (0.77 of the HBM roofline at B = 65536), 1 CTA of 8 warps and
+//     252 registers for K = 10 (0.60).
+//   * energy_pair_kernel (class-tiled, warp pairs; K <= 10, both tables, B >= 64 x SMs, the default for K >= 5): the tables
+//     live in SHARED memory as interleaved pairs, a warp pair owns a 4-row batch in registers, reductions are shuffles only
+//     -- 0.72 at K = 10.
+// Per sample the tile kernels move f once from HBM and grad once to HBM and nothing else.
 // HBM roofline: compulsory traffic is f (read) + grad_f (write) = 2*D*4 bytes per sample (+ the tables once).
 #include "dd_common.cuh"
 #include "dd_stream.cuh"

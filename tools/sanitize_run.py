@@ -51,6 +51,14 @@ def main():
                 for nf in (False, True):
                     ops.energy_fwd_bwd(f, y, gp, lp, 1.0, 1.0, nf, mode=mode)
         ops.energy_fwd_bwd(f[:, :512].contiguous(), y, gp[:, :512].contiguous(), None, 1.0, 1.0, False, mode="tile")   # generic (non-FULL) path
+        # warp-pair kernel, generic D (predicated chunks), odd K (zero-padded pair), an out-of-range target, ragged last batches
+        C, K, D, B = 5, 5, 520, 203
+        gp = torch.nn.functional.normalize(torch.randn(C, D, device=dev, generator=g), dim=-1)
+        lp = torch.nn.functional.normalize(torch.randn(C, K, D, device=dev, generator=g), dim=-1)
+        f = torch.randn(B, D, device=dev, generator=g); y = torch.randint(0, C, (B,), device=dev, generator=g); y[17] = C
+        f[:3] = lp[y[:3].clamp(max=C - 1), 1]
+        for nf in (False, True):
+            ops.energy_fwd_bwd(f, y, gp, lp, 1.0, 1.0, nf, mode="tile_pair")
     if want("K8"):   # K8 fwd / bwd, K9
         img = torch.randn(2, 3, 128, 160, device=dev, generator=g)
         out = ops.bicubic_resize(img, (56, 70)); ops.bicubic_resize_bwd(out, (128, 160))

@@ -298,9 +298,10 @@ bicubic_fwd_vec_kernel(const T* __restrict__ in, T* __restrict__ out, int Hin, i
 // (39 % of the instructions of bicubic_fwd_vec_kernel), and the copy of a CTA overlaps the passes of its SM neighbours.
 // The box starts at the VIRTUAL coordinate of the first tap (it may be negative, or run past the image): the TMA unit
 // zero-fills what lies outside, and edge tiles then replicate the border row / column into those cells (ATen clamps the
-// tap index).  The box IS the staged region (RW = 4 * odd floats keeps pass 1's 16-byte row accesses conflict-free).
-// fp32 only: for 16-bit storage the box would land as raw 16-bit rows and need a conversion sweep into the fp32 region,
-// which measured slower (0.160 ms at B = 128) than converting while staging with plain loads (bicubic_fwd_vec_kernel, 0.152 ms).
+// tap index).  The box IS the staged region, in the storage type: fp32 rows of 4 * odd floats, 16-bit rows of 8 * odd elements
+// (an odd number of 16-byte units keeps pass 1's LDS.128 along rows conflict-free); 16-bit values are converted in pass 1's
+// registers (a conversion sweep into an fp32 region measured slower than the plain-load kernel: 0.160 vs 0.152 ms at
+// B = 128; reading the raw box directly takes 0.120 ms).
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
                      smem_u32(smem_dst)),
@@ -308,13 +309,43 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* t
                  : "memory");
 }
 
+// 16-bit storage: pass 1 reads the raw box.  Rows lane, lane+32, ... of one output column; the 4 taps start SH elements into
+// the aligned 8-element vector pair (lo, hi): one LDS.128 (two when the taps straddle the vectors), conflict-free because the
+// row pitch is 8 * odd elements = an odd number of 16-byte units.
+template <typename T> __device__ __forceinline__ float bits16_to_f32(uint32_t b);
+template <> __device__ __forceinline__ float bits16_to_f32<__half>(uint32_t b) { return __half2float(__ushort_as_half((unsigned short)b)); }
+template <> __device__ __forceinline__ float bits16_to_f32<__nv_bfloat16>(uint32_t b) { return __uint_as_float(b << 16); }
+__device__ __forceinline__ uint4 lds128u(const void* p) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+    return v;
+}
+template <typename T, int SH>
+__device__ __forceinline__ void interp_rows16(const T* __restrict__ rcol, float* __restrict__ trow, int nrow, int S, const float4& c) {
+    for (int i = 0; i < nrow; i += 32) {
+        const uint4 lo = lds128u(rcol);
+        uint4 hi = make_uint4(0u, 0u, 0u, 0u);
+        if (SH > 4) hi = lds128u(rcol + 8);
+        const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+        float e[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int j = SH + t;
+            e[t] = bits16_to_f32<T>((j & 1) ? (w[j >> 1] >> 16) : (w[j >> 1] & 0xffffu));
+        }
+        *trow = e[0] * c.x + e[1] * c.y + e[2] * c.z + e[3] * c.w;
+        rcol += 32 * S;
+        trow += 32;
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(RS_THREADS)
 bicubic_fwd_tma_kernel(const __grid_constant__ CUtensorMap tm, T* __restrict__ out, int Hin, int Win, int Hout, int Wout, float sy,
-                       float sx, int S /* fp32 region row stride, 4 * odd */,
-                       int RWB /* box width (elements) */, int rh_max, int tp) {
+                       float sx, int S /* region row pitch in elements: 4 * odd (fp32), 8 * odd (16-bit) */,
+                       int RWB /* box width (elements) = S */, int rh_max, int tp) {
     extern __shared__ __align__(128) unsigned char smraw[];
-    static_assert(sizeof(T) == 4, "fp32 storage only");
+    constexpr bool F32 = sizeof(T) == 4;
     constexpr int VN = Vec16<T>::N;
     // One tile per CTA; the copies of a CTA's SM neighbours overlap its passes.  (A persistent variant with two boxes per CTA
     // and the next tile's copy in flight was measured SLOWER, 0.128 vs 0.111 ms at B = 128 fp32: the kernel is bound by the
@@ -363,28 +394,29 @@ bicubic_fwd_tma_kernel(const __grid_constant__ CUtensorMap tm, T* __restrict__ o
         }
         __syncthreads();            // barriers initialised (first iteration) and tap tables written before anyone goes on
         mbar_wait<20>(&bar[0], 0);
-        float* region = reinterpret_cast<float*>(smraw);
+        T* region = reinterpret_cast<T*>(smraw);                      // the box in its storage type
         const bool edge_y = vy_lo < 0 || vy_lo + rh > Hin, edge_x = vx_lo < 0 || vx_hi >= Win;
         if (edge_y) {               // replicate the first / last image row into the virtual rows outside (whole staged width)
             const int r_first = -vy_lo, r_last = Hin - 1 - vy_lo;     // staged rows of image rows 0 and Hin - 1
             const int n_top = vy_lo < 0 ? r_first : 0, n_bot = r_last < rh - 1 ? rh - 1 - r_last : 0;
-            for (int i = tid; i < (n_top + n_bot) * (S / 4); i += RS_THREADS) {
-                const int q = i / (S / 4), c4 = i - q * (S / 4);
+            const int cpr = S / VN;                                    // 16-byte chunks per staged row
+            for (int i = tid; i < (n_top + n_bot) * cpr; i += RS_THREADS) {
+                const int q = i / cpr, c4 = i - q * cpr;
                 const int ry = q < n_top ? q : r_last + 1 + (q - n_top);
-                reinterpret_cast<float4*>(region + ry * S)[c4] = reinterpret_cast<const float4*>(region + (q < n_top ? r_first : r_last) * S)[c4];
+                reinterpret_cast<uint4*>(region + ry * S)[c4] = reinterpret_cast<const uint4*>(region + (q < n_top ? r_first : r_last) * S)[c4];
             }
             __syncthreads();
         }
         if (edge_x) {               // then the border columns (corners come out right: the rows are already replicated)
             const int c_first = -xa, c_last = Win - 1 - xa;
             for (int ry = tid; ry < rh; ry += RS_THREADS) {
-                float* drow = region + ry * S;
+                T* drow = region + ry * S;
                 if (vx_lo < 0) {
-                    const float e = drow[c_first];
+                    const T e = drow[c_first];
                     for (int cx = 0; cx < c_first; ++cx) drow[cx] = e;
                 }
                 if (vx_hi >= Win) {
-                    const float e = drow[c_last];
+                    const T e = drow[c_last];
                     for (int cx = c_last + 1; cx <= vx_hi - xa; ++cx) drow[cx] = e;
                 }
             }
@@ -398,14 +430,28 @@ bicubic_fwd_tma_kernel(const __grid_constant__ CUtensorMap tm, T* __restrict__ o
                 if (l >= nx) break;
                 const float4 c = tx_c[l];
                 const int x0 = tx_0[l];
-                const float* rcol = region + (x0 & ~3) + lane * S;
                 float* trow = tmpT + l * tp + lane;
                 const int nrow = rh - lane;
-                switch (x0 & 3) {                                          // warp-uniform: the row loop is specialised per shift
-                    case 0: interp_rows<0>(rcol, trow, nrow, S, c); break;
-                    case 1: interp_rows<1>(rcol, trow, nrow, S, c); break;
-                    case 2: interp_rows<2>(rcol, trow, nrow, S, c); break;
-                    default: interp_rows<3>(rcol, trow, nrow, S, c); break;
+                if constexpr (F32) {
+                    const float* rcol = reinterpret_cast<const float*>(region) + (x0 & ~3) + lane * S;
+                    switch (x0 & 3) {                                      // warp-uniform: the row loop is specialised per shift
+                        case 0: interp_rows<0>(rcol, trow, nrow, S, c); break;
+                        case 1: interp_rows<1>(rcol, trow, nrow, S, c); break;
+                        case 2: interp_rows<2>(rcol, trow, nrow, S, c); break;
+                        default: interp_rows<3>(rcol, trow, nrow, S, c); break;
+                    }
+                } else {
+                    const T* rcol = region + (x0 & ~7) + lane * S;
+                    switch (x0 & 7) {
+                        case 0: interp_rows16<T, 0>(rcol, trow, nrow, S, c); break;
+                        case 1: interp_rows16<T, 1>(rcol, trow, nrow, S, c); break;
+                        case 2: interp_rows16<T, 2>(rcol, trow, nrow, S, c); break;
+                        case 3: interp_rows16<T, 3>(rcol, trow, nrow, S, c); break;
+                        case 4: interp_rows16<T, 4>(rcol, trow, nrow, S, c); break;
+                        case 5: interp_rows16<T, 5>(rcol, trow, nrow, S, c); break;
+                        case 6: interp_rows16<T, 6>(rcol, trow, nrow, S, c); break;
+                        default: interp_rows16<T, 7>(rcol, trow, nrow, S, c); break;
+                    }
                 }
             }
         }
@@ -783,19 +829,18 @@ static int launch_fwd(const void* in, void* out, int64_t planes, int Hin, int Wi
     const int tiles_x = (Wout + RS_TO - 1) / RS_TO, tiles_y = (Hout + RS_TO - 1) / RS_TO;
     const int64_t blocks = planes * tiles_x * tiles_y;
     DD_REQUIRE(blocks < (1ll << 31), DD_EUNSUPPORTED, "dd_bicubic_resize_fwd: too many tiles");
-    if constexpr (sizeof(T) == 4) {
-        if (!getenv("DD_K8_NO_TMA")) {   // tensor-map staging (DD_K8_NO_TMA: development switch back to the load/store staging below)
-            const int S = (((rw + (VN - 1) + 4 + 3) / 4) | 1) * 4;  // alignment slack + span + the second float4 of the last tap, 4 * odd
-            const size_t box_bytes = ((size_t)rh * S * sizeof(T) + 127) / 128 * 128;
-            const size_t smem = box_bytes + (((size_t)RS_TO * tp + 3) / 4 * 4 + RS_TO * 10) * sizeof(float) + 16;
-            CUtensorMap tm;
-            if (smem <= 100 * 1024 && planes <= 65535 && tiles_y <= 65535 && make_plane_map<T>(&tm, in, planes, Hin, Win, S, rh)) {
-                auto kern = bicubic_fwd_tma_kernel<T>;
-                DD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                kern<<<dim3(tiles_x, tiles_y, (unsigned)planes), RS_THREADS, smem, st>>>(tm, (T*)out, Hin, Win, Hout, Wout, sy, sx, S, S, rh, tp);
-                DD_LAUNCH_OK();
-                return 0;
-            }
+    if (!getenv("DD_K8_NO_TMA")) {   // tensor-map staging (DD_K8_NO_TMA: development switch back to the load/store staging below)
+        // row pitch = box width: alignment slack (VN - 1) + span + the second vector of the last tap; an ODD number of 16-byte units
+        const int S = sizeof(T) == 4 ? (((rw + (VN - 1) + 4 + 3) / 4) | 1) * 4 : (((rw + (VN - 1) + 12 + 7) / 8) | 1) * 8;
+        const size_t box_bytes = ((size_t)rh * S * sizeof(T) + 127) / 128 * 128;
+        const size_t smem = box_bytes + (((size_t)RS_TO * tp + 3) / 4 * 4 + RS_TO * 10) * sizeof(float) + 16;
+        CUtensorMap tm;
+        if (smem <= 100 * 1024 && planes <= 65535 && tiles_y <= 65535 && make_plane_map<T>(&tm, in, planes, Hin, Win, S, rh)) {
+            auto kern = bicubic_fwd_tma_kernel<T>;
+            DD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<dim3(tiles_x, tiles_y, (unsigned)planes), RS_THREADS, smem, st>>>(tm, (T*)out, Hin, Win, Hout, Wout, sy, sx, S, S, rh, tp);
+            DD_LAUNCH_OK();
+            return 0;
         }
     }
     if ((Win % VN == 0) && aligned16(in)) {

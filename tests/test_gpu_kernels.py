@@ -576,8 +576,8 @@ def test_bicubic_resize_bwd(ops, cuda_device, shape, size):
 
 
 def test_bicubic_tma_staging_matches_plain_staging(ops, cuda_device, monkeypatch):
-    """fp32 forward / backward: the tensor-map (TMA) staged kernels and the load/store staged ones they replace give the same
-    bits (same two passes, same order), edge tiles included; DD_K8_NO_TMA is the library's development switch."""
+    """fp32 forward / backward and 16-bit forward: the tensor-map (TMA) staged kernels and the load/store staged ones they
+    replace give the same bits (same two passes, same order), edge tiles included; DD_K8_NO_TMA is the library's development switch."""
     x = torch.randn(3, 3, 512, 512, generator=_g(31)).to(cuda_device)
     g = torch.randn(3, 3, 224, 224, generator=_g(32)).to(cuda_device)
     small = torch.randn(2, 1, 64, 48, generator=_g(33)).to(cuda_device)
@@ -585,7 +585,9 @@ def test_bicubic_tma_staging_matches_plain_staging(ops, cuda_device, monkeypatch
     for no_tma in ("", "1"):
         if no_tma:
             monkeypatch.setenv("DD_K8_NO_TMA", no_tma)
-        outs.append((ops.bicubic_resize(x, (224, 224)), ops.bicubic_resize_bwd(g, (512, 512)), ops.bicubic_resize(small, (20, 30))))
+        outs.append((ops.bicubic_resize(x, (224, 224)), ops.bicubic_resize_bwd(g, (512, 512)), ops.bicubic_resize(small, (20, 30)),
+                     ops.bicubic_resize(x.half(), (224, 224)), ops.bicubic_resize(x.bfloat16(), (224, 224)),
+                     ops.bicubic_resize(small[..., :40].contiguous().half(), (30, 25))))
     for a, b in zip(*outs):
         assert torch.equal(a, b)
 

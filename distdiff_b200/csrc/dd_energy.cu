@@ -362,12 +362,6 @@ class_sort_kernel(const int64_t* __restrict__ target, int B, int C, int* __restr
 #ifndef DD_K4_R_LARGE
 #define DD_K4_R_LARGE 4
 #endif
-#ifndef DD_K4_SPLIT_RS
-#define DD_K4_SPLIT_RS 2
-#endif
-#ifndef DD_K4_SPLIT_MINK
-#define DD_K4_SPLIT_MINK 99   // smallest KT whose group prototypes are split over two thread groups (TileCfg::NG); measured slower, off
-#endif
 __host__ __device__ constexpr int et_rows(int KT) { return KT <= 4 ? DD_K4_R_SMALL : DD_K4_R_LARGE; }
 
 // Warp sum of S packed (float2) partials per lane through a warp-private shared-memory transposition: every lane
@@ -409,46 +403,38 @@ __device__ __forceinline__ float2 tr_reduce(const float2 (&v)[S], float2* tr, in
     return t;
 }
 
-// NG thread groups of 256 threads share a batch.  NG = 1: every thread holds all KT prototype slices (+ g) of its 8 columns
-// (8 (KT+1) registers): KT <= 4 runs two CTAs per SM.  NG = 2 (KT >= 5): the group prototypes are SPLIT over two groups --
-// group 0 holds l_0..l_{KH-1} and reduces <f,g> with them, group 1 holds l_KH..l_{KT-1} and reduces |f|^2, both hold g --
-// so a thread reduces half the values per row, the kernel fits 128 registers and 16 warps (not 8) hide its latencies.
-// The gradient row of a sample is written by the group that holds its l*.
+// (Tried and dropped: splitting the K prototypes over two 256-thread groups so that the kernel fits 128 registers and 16 warps
+// at K >= 5 -- 0.35 of the HBM roofline at K = 10 against 0.59: every warp finishes every batch redundantly, so the instruction
+// count doubled with the warps.  The warp-pair kernel below is what K >= 5 uses instead.)
 template <int KT>
 struct TileCfg {
     static constexpr int R = et_rows(KT);
-    static constexpr int NG = KT >= DD_K4_SPLIT_MINK ? 2 : 1;
-    static constexpr int THREADS = NG * PK_THREADS;
-    static constexpr int NW = NG * PK_WARPS;
-    static constexpr int KH = KT / NG;                       // group prototypes per thread group
-    static constexpr int NX = NG == 1 ? 2 : 1;               // extra reduced values per row and group: <f,g>, |f|^2
-    static constexpr int NV = KH + NX;                       // reduced values per row and group in pass 1
+    static constexpr int NV = KT + 2;                        // reduced values per row in pass 1: K dots, <f,g>, |f|^2
     static constexpr int SP1 = (NV + 1) / 2;                 // ... packed in pairs
-    static constexpr int RS0 = (32 / SP1) >= R ? R : (32 / SP1);
-    static constexpr int RS = (NG == 2 && RS0 > DD_K4_SPLIT_RS) ? DD_K4_SPLIT_RS : RS0;   // rows per reduction round (split kernels: register budget)
+    static constexpr int RS = (32 / SP1) >= R ? R : (32 / SP1);   // rows per reduction round
     static constexpr int NSUB = (R + RS - 1) / RS;
     static constexpr int S1 = RS * SP1;                      // slots per round
     static constexpr int S2 = R * 2;                         // exact pass: (|fn-g|^2, |fn-l*|^2), (<f,g-fn>, <f,l*-fn>) per row
-    static constexpr int SPN = (KH + 2) / 2;                 // prototype norms per group: |l_k|^2 (KH of them), |g|^2
+    static constexpr int SPN = (KT + 2) / 2;                 // prototype norms: |l_k|^2 (k < KT), |g|^2
     static constexpr int TR_A = TrCfg<S1>::FLOAT2S > TrCfg<S2>::FLOAT2S ? TrCfg<S1>::FLOAT2S : TrCfg<S2>::FLOAT2S;
     static constexpr int TR_FLOAT2S = TR_A > TrCfg<SPN>::FLOAT2S ? TR_A : TrCfg<SPN>::FLOAT2S;
     static constexpr int CTAS_PER_SM = (KT <= 4 && R <= 4) ? 2 : 1;
-    static constexpr size_t SMEM_FIXED = PK_MAX_STAGES * sizeof(uint64_t) + (size_t)NW * TR_FLOAT2S * sizeof(float2) +
-                                         (size_t)NW * (2 * NSUB + 1) * 32 * sizeof(float2);
-    static_assert(KT % NG == 0 && SP1 <= 32 && SPN <= 16 && S2 <= 32, "unsupported KT");
+    static constexpr size_t SMEM_FIXED = PK_MAX_STAGES * sizeof(uint64_t) + (size_t)PK_WARPS * TR_FLOAT2S * sizeof(float2) +
+                                         (size_t)PK_WARPS * (2 * NSUB + 1) * 32 * sizeof(float2);
+    static_assert(SP1 <= 32 && S2 <= 32, "unsupported KT");
 };
 
 // run body(p) with p = the K-th prototype slice, K CTA-uniform: a tree of uniform branches around COPIES of the body,
 // so the selected registers are used in place (a register array cannot be indexed at run time without going through
 // local memory, and copying 8 registers per selection costs as much as the arithmetic that follows)
-template <int KN, int LO, int HI, typename F>
-__device__ __forceinline__ void with_proto(const float4 (&l8)[KN][PK_CH], int k, F&& body) {
+template <int KT, int LO, int HI, typename F>
+__device__ __forceinline__ void with_proto(const float4 (&l8)[KT][PK_CH], int k, F&& body) {
     if constexpr (HI - LO == 1) {
         body(l8[LO]);
     } else {
         constexpr int MID = (LO + HI) / 2;
-        if (k < MID) with_proto<KN, LO, MID>(l8, k, body);
-        else with_proto<KN, MID, HI>(l8, k, body);
+        if (k < MID) with_proto<KT, LO, MID>(l8, k, body);
+        else with_proto<KT, MID, HI>(l8, k, body);
     }
 }
 
@@ -457,51 +443,41 @@ __device__ __forceinline__ float2 hi2(const float4& v) { return make_float2(v.z,
 __device__ __forceinline__ float2 dot4_first(const float4& a, const float4& b) {
     return ffma2(hi2(a), hi2(b), fmul2(lo2(a), lo2(b)));
 }
-__device__ __forceinline__ float dot8(const float4 (&a)[PK_CH], const float4 (&b)[PK_CH]) {
-    float2 s = dot4_first(a[0], b[0]);
-#pragma unroll
-    for (int ch = 1; ch < PK_CH; ++ch) s = dot4(a[ch], b[ch], s);
-    return s.x + s.y;
-}
 
 // One batch = <= R samples of one class.  Per batch and thread (8 owned columns):
-//   pass 1   the group's dots <f,l_k>, <f,g> / |f|^2 against the register-resident prototype slices -> warp transposition
-//            -> one shared-memory hop across the warps (ONE __syncthreads per batch);
+//   pass 1   K dots <f,l_k>, <f,g>, |f|^2 against the register-resident prototype slices -> warp transposition ->
+//            one shared-memory hop across the 8 warps (ONE __syncthreads per batch);
 //   finish   (lane r finishes row r, every warp redundantly) k* = first argmax, s = 1/||f||, and the two distances
 //            from the dots:  ||fn-p||^2 = |fn|^2 - 2 s <f,p> + |p|^2  (|p|^2 reduced once per class run);
 //   exact    only if some distance of the batch is so small that the expansion loses accuracy
 //            (d^2 < (|fn|^2+|p|^2)/8, e.g. f on its prototype): direct sums of (p - fn)^2 like the reference,
 //            one more reduction round + barrier.  CTA-uniform decision;
-//   pass 3   grad = A f + Bg g + Bl l*  (the chain rule through f/||f|| folded into the three coefficients),
-//            by the thread group that holds l*.
+//   pass 3   grad = A f + Bg g + Bl l*  (the chain rule through f/||f|| folded into the three coefficients).
 // FULL: D == 2048 (every thread owns both of its chunks), K == KT, both prototype tables present -> no predicates
 template <int KT, bool FULL>
-__global__ void __launch_bounds__(TileCfg<KT>::THREADS, TileCfg<KT>::CTAS_PER_SM)
+__global__ void __launch_bounds__(EN_THREADS, TileCfg<KT>::CTAS_PER_SM)
 energy_tile_kernel(const float* __restrict__ f, const int* __restrict__ perm, const int* __restrict__ off,
                    const float* __restrict__ g, const float* __restrict__ l, int B, int D_, int C, int K_, float gs, float ls,
                    int normalize_f, float* __restrict__ score, float* __restrict__ per_sample, int32_t* __restrict__ kstar_out,
                    float* __restrict__ grad_f, unsigned int* __restrict__ ticket, int stages) {
     using Cfg = TileCfg<KT>;
-    constexpr int R = Cfg::R, NG = Cfg::NG, NW = Cfg::NW, KH = Cfg::KH, NV = Cfg::NV, SP1 = Cfg::SP1, RS = Cfg::RS, NSUB = Cfg::NSUB,
-                  S1 = Cfg::S1, S2 = Cfg::S2, SPN = Cfg::SPN, THREADS = Cfg::THREADS;
+    constexpr int R = Cfg::R, NV = Cfg::NV, SP1 = Cfg::SP1, RS = Cfg::RS, NSUB = Cfg::NSUB, S1 = Cfg::S1, S2 = Cfg::S2, SPN = Cfg::SPN;
+    static_assert(SP1 <= 32, "KT too large");
     const int D = FULL ? PK_MAX_D : D_;
     const int K = FULL ? KT : K_;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int stage_elems = R * D;
     float* ring = reinterpret_cast<float*>(smem_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)stages * stage_elems * sizeof(float));
-    float2* tr_all = reinterpret_cast<float2*>(full + PK_MAX_STAGES);          // [NW][TR_FLOAT2S]
+    float2* tr_all = reinterpret_cast<float2*>(full + PK_MAX_STAGES);          // [PK_WARPS][TR_FLOAT2S]
     // cross1 is double-buffered by batch parity: with one barrier per batch a fast warp writes the partials of batch
     // i+1 while a slow one still reads those of batch i (it cannot get two batches ahead)
-    float2* cross1_all = tr_all + NW * Cfg::TR_FLOAT2S;                       // [2][NW][NSUB][32]
-    float2* cross2 = cross1_all + 2 * NW * NSUB * 32;                         // [NW][32]
-    __shared__ float fin[THREADS];
+    float2* cross1_all = tr_all + PK_WARPS * Cfg::TR_FLOAT2S;                 // [2][PK_WARPS][NSUB][32]
+    float2* cross2 = cross1_all + 2 * PK_WARPS * NSUB * 32;                   // [PK_WARPS][32]
+    __shared__ float fin[EN_THREADS];
     __shared__ bool is_last;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int grp = NG == 1 ? 0 : tid / PK_THREADS;     // thread group (warp-uniform)
-    const int t = NG == 1 ? tid : tid % PK_THREADS;     // column owner index inside the group
-    const int k0 = grp * KH;                            // first group prototype held by this thread group
     float2* tr = tr_all + warp * Cfg::TR_FLOAT2S;
     const int G = gridDim.x, gi = blockIdx.x;
     const int r0 = (int)((int64_t)B * gi / G), r1 = (int)((int64_t)B * (gi + 1) / G);
@@ -509,7 +485,7 @@ energy_tile_kernel(const float* __restrict__ f, const int* __restrict__ perm, co
     int chunk[PK_CH];
     bool own[PK_CH];
 #pragma unroll
-    for (int ch = 0; ch < PK_CH; ++ch) { chunk[ch] = t + ch * PK_THREADS; own[ch] = FULL || chunk[ch] < nch; }
+    for (int ch = 0; ch < PK_CH; ++ch) { chunk[ch] = tid + ch * PK_THREADS; own[ch] = FULL || chunk[ch] < nch; }
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     const bool has_g = FULL || g != nullptr, has_l = FULL || l != nullptr;
     const float invB = 1.f / (float)B;
@@ -549,11 +525,8 @@ energy_tile_kernel(const float* __restrict__ f, const int* __restrict__ perm, co
             issue(s, bn, lane < bn ? __ldg(perm + br + lane) : 0);
         }
     }
-    float4 g8[PK_CH], l8[KH][PK_CH];
-    // lane q < SPN: (|p_2q|^2, |p_2q+1|^2) of thread group j in pn[j], p = the group's l_k0 .. l_k0+KH-1, then g
-    float2 pn[NG];
-#pragma unroll
-    for (int j = 0; j < NG; ++j) pn[j] = make_float2(0.f, 0.f);
+    float4 g8[PK_CH], l8[KT][PK_CH];
+    float2 pn = make_float2(0.f, 0.f);   // lane q: (|p_2q|^2, |p_2q+1|^2), p = l_0 .. l_KT-1, g
     int cur = -1;
     int s = 0, flip = 0;
     uint32_t parity = 0;
@@ -575,7 +548,7 @@ energy_tile_kernel(const float* __restrict__ f, const int* __restrict__ perm, co
         const int orig_l = n_orig;                        // lane r: original index of row r
         const int rf_n = n_rf, rf_src = n_rf_src;
         const bool valid = bc < C;   // bucket C = out-of-range targets
-        float2* cross1 = cross1_all + flip * (NW * NSUB * 32);
+        float2* cross1 = cross1_all + flip * (PK_WARPS * NSUB * 32);
         flip ^= 1;
         if (bc != cur && valid) {   // new class run: prototype slices into registers, their squared norms into `pn`
             cur = bc;
@@ -583,31 +556,38 @@ energy_tile_kernel(const float* __restrict__ f, const int* __restrict__ perm, co
             for (int ch = 0; ch < PK_CH; ++ch) {
                 g8[ch] = (has_g && own[ch]) ? __ldg(reinterpret_cast<const float4*>(g + (int64_t)bc * D) + chunk[ch]) : zero4;
 #pragma unroll
-                for (int k = 0; k < KH; ++k)
-                    l8[k][ch] = (has_l && (FULL || k0 + k < K) && own[ch])
-                                    ? __ldg(reinterpret_cast<const float4*>(l + ((int64_t)bc * K + k0 + k) * D) + chunk[ch]) : zero4;
+                for (int k = 0; k < KT; ++k)
+                    l8[k][ch] = (has_l && (FULL || k < K) && own[ch])
+                                    ? __ldg(reinterpret_cast<const float4*>(l + ((int64_t)bc * K + k) * D) + chunk[ch]) : zero4;
             }
             float nn[2 * SPN];
 #pragma unroll
             for (int j = 0; j < 2 * SPN; ++j) nn[j] = 0.f;
 #pragma unroll
-            for (int k = 0; k < KH; ++k) nn[k] = dot8(l8[k], l8[k]);
-            nn[KH] = dot8(g8, g8);
+            for (int k = 0; k < KT; ++k) {
+                float2 a = dot4_first(l8[k][0], l8[k][0]);
+#pragma unroll
+                for (int ch = 1; ch < PK_CH; ++ch) a = dot4(l8[k][ch], l8[k][ch], a);
+                nn[k] = a.x + a.y;
+            }
+            {
+                float2 a = dot4_first(g8[0], g8[0]);
+#pragma unroll
+                for (int ch = 1; ch < PK_CH; ++ch) a = dot4(g8[ch], g8[ch], a);
+                nn[KT] = a.x + a.y;
+            }
             float2 vn[SPN];
 #pragma unroll
             for (int q = 0; q < SPN; ++q) vn[q] = make_float2(nn[2 * q], nn[2 * q + 1]);
-            const float2 tn = tr_reduce<SPN>(vn, tr, lane);
+            const float2 t = tr_reduce<SPN>(vn, tr, lane);
             __syncthreads();   // cross2 may still be read by a slow warp of the previous batch's exact pass
-            if (lane % TrCfg<SPN>::LPS == 0 && lane / TrCfg<SPN>::LPS < SPN) cross2[warp * 32 + lane / TrCfg<SPN>::LPS] = tn;
+            if (lane % TrCfg<SPN>::LPS == 0 && lane / TrCfg<SPN>::LPS < SPN) cross2[warp * 32 + lane / TrCfg<SPN>::LPS] = t;
             __syncthreads();
+            pn = make_float2(0.f, 0.f);
+            if (lane < SPN) {
+                pn = cross2[lane];
 #pragma unroll
-            for (int j = 0; j < NG; ++j) {
-                pn[j] = make_float2(0.f, 0.f);
-                if (lane < SPN) {
-                    pn[j] = cross2[(j * PK_WARPS) * 32 + lane];
-#pragma unroll
-                    for (int w = 1; w < PK_WARPS; ++w) pn[j] = fadd2(pn[j], cross2[(j * PK_WARPS + w) * 32 + lane]);
-                }
+                for (int w = 1; w < PK_WARPS; ++w) pn = fadd2(pn, cross2[w * 32 + lane]);
             }   // (the next write to cross2 is behind this batch's pass-1 barrier)
         }
         mbar_wait(&full[s], parity);
@@ -621,7 +601,7 @@ energy_tile_kernel(const float* __restrict__ f, const int* __restrict__ perm, co
                 else xv[r][ch] = own[ch] ? *reinterpret_cast<const float4*>(st + r * D + chunk[ch] * 4) : zero4;
             }
 
-        // ---- pass 1: the group's <f,l_k>, then <f,g> and/or |f|^2 of the raw rows, packed in pairs, RS rows per round ----
+        // ---- pass 1: <f,l_k>, <f,g>, |f|^2 of the raw rows, packed in pairs, RS rows per transposition round ----
 #pragma unroll
         for (int h = 0; h < NSUB; ++h) {
             float2 v[S1];
@@ -633,21 +613,27 @@ energy_tile_kernel(const float* __restrict__ f, const int* __restrict__ perm, co
                 for (int j = 0; j < 2 * SP1; ++j) d[j] = 0.f;
                 if (r < R) {
 #pragma unroll
-                    for (int k = 0; k < KH; ++k)
-                        if (FULL || k0 + k < K) d[k] = dot8(xv[r], l8[k]);
-                    if constexpr (NG == 1) {
-                        d[KH] = dot8(xv[r], g8);
-                        d[KH + 1] = dot8(xv[r], xv[r]);
-                    } else {
-                        if (grp == 0) d[KH] = dot8(xv[r], g8);
-                        else d[KH] = dot8(xv[r], xv[r]);
+                    for (int k = 0; k < KT; ++k) {
+                        if (FULL || k < K) {
+                            float2 a = dot4_first(xv[r][0], l8[k][0]);
+#pragma unroll
+                            for (int ch = 1; ch < PK_CH; ++ch) a = dot4(xv[r][ch], l8[k][ch], a);
+                            d[k] = a.x + a.y;
+                        }
+                    }
+                    {
+                        float2 a = dot4_first(xv[r][0], g8[0]), b = dot4_first(xv[r][0], xv[r][0]);
+#pragma unroll
+                        for (int ch = 1; ch < PK_CH; ++ch) { a = dot4(xv[r][ch], g8[ch], a); b = dot4(xv[r][ch], xv[r][ch], b); }
+                        d[KT] = a.x + a.y;
+                        d[KT + 1] = b.x + b.y;
                     }
                 }
 #pragma unroll
                 for (int q = 0; q < SP1; ++q) v[rr * SP1 + q] = make_float2(d[2 * q], d[2 * q + 1]);
             }
-            const float2 tp = tr_reduce<S1>(v, tr, lane);
-            if (lane % TrCfg<S1>::LPS == 0 && lane / TrCfg<S1>::LPS < S1) cross1[(warp * NSUB + h) * 32 + lane / TrCfg<S1>::LPS] = tp;
+            const float2 t = tr_reduce<S1>(v, tr, lane);
+            if (lane % TrCfg<S1>::LPS == 0 && lane / TrCfg<S1>::LPS < S1) cross1[(warp * NSUB + h) * 32 + lane / TrCfg<S1>::LPS] = t;
         }
         __syncthreads();
         // every thread holds the batch in registers: refill the stage
@@ -656,49 +642,37 @@ energy_tile_kernel(const float* __restrict__ f, const int* __restrict__ perm, co
         // ---- finish: lane r < R handles row r (every warp redundantly; no second barrier needed) ----
         const int my_r = lane < R ? lane : 0;
         const int my_h = my_r / RS, my_base = (my_r % RS) * SP1;
-        float dk[NG][2 * SP1];
+        float dk[2 * SP1];
 #pragma unroll
-        for (int j = 0; j < NG; ++j)
-#pragma unroll
-            for (int i = 0; i < 2 * SP1; ++i) dk[j][i] = 0.f;
+        for (int j = 0; j < 2 * SP1; ++j) dk[j] = 0.f;
 #pragma unroll
         for (int h = 0; h < NSUB; ++h) {
+            float2 tot = make_float2(0.f, 0.f);
+            if (lane < S1) {
+                tot = cross1[(0 * NSUB + h) * 32 + lane];
 #pragma unroll
-            for (int j = 0; j < NG; ++j) {
-                float2 tot = make_float2(0.f, 0.f);
-                if (lane < S1) {
-                    tot = cross1[((j * PK_WARPS) * NSUB + h) * 32 + lane];
+                for (int w = 1; w < PK_WARPS; ++w) tot = fadd2(tot, cross1[(w * NSUB + h) * 32 + lane]);   // fixed order
+            }
 #pragma unroll
-                    for (int w = 1; w < PK_WARPS; ++w) tot = fadd2(tot, cross1[((j * PK_WARPS + w) * NSUB + h) * 32 + lane]);   // fixed order
-                }
-#pragma unroll
-                for (int q = 0; q < SP1; ++q) {
-                    const float tx = __shfl_sync(0xffffffffu, tot.x, my_base + q), ty = __shfl_sync(0xffffffffu, tot.y, my_base + q);
-                    if (NSUB == 1 || my_h == h) { dk[j][2 * q] = tx; dk[j][2 * q + 1] = ty; }
-                }
+            for (int q = 0; q < SP1; ++q) {
+                const float tx = __shfl_sync(0xffffffffu, tot.x, my_base + q), ty = __shfl_sync(0xffffffffu, tot.y, my_base + q);
+                if (NSUB == 1 || my_h == h) { dk[2 * q] = tx; dk[2 * q + 1] = ty; }
             }
         }
         int ks = 0;
-        float fl = dk[0][0];   // <f, l*>
+        float fl = dk[0];   // <f, l*>
         if (has_l) {
 #pragma unroll
-            for (int k = 1; k < KT; ++k) {
-                const float dv = dk[k / KH][k % KH];
-                if ((FULL || k < K) && dv > fl) { fl = dv; ks = k; }   // strict > : first max wins, like torch.argmax
-            }
+            for (int k = 1; k < KT; ++k)
+                if ((FULL || k < K) && dk[k] > fl) { fl = dk[k]; ks = k; }   // strict > : first max wins, like torch.argmax
         }
-        const float fg = dk[0][KH], ff = NG == 1 ? dk[0][KH + 1] : dk[NG - 1][KH];
+        const float fg = dk[KT], ff = dk[KT + 1];
         // generate_data.py:747  f / f.norm(dim=-1, keepdim=True): applied as a per-row scale s = 1/||f||
         const float s_l = normalize_f ? rsqrtf(ff) : 1.f;
         const float fn2 = s_l * s_l * ff;                                      // |fn|^2
-        const int kk = ks % KH;                                                // index of l* inside its thread group
-        float nl = 0.f;                                                        // |l*|^2
-#pragma unroll
-        for (int j = 0; j < NG; ++j) {
-            const float nx = __shfl_sync(0xffffffffu, pn[j].x, kk >> 1), ny = __shfl_sync(0xffffffffu, pn[j].y, kk >> 1);
-            if (NG == 1 || ks / KH == j) nl = (kk & 1) ? ny : nx;
-        }
-        const float ng = __shfl_sync(0xffffffffu, (KH & 1) ? pn[0].y : pn[0].x, KH >> 1);   // |g|^2
+        const float nlx = __shfl_sync(0xffffffffu, pn.x, ks >> 1), nly = __shfl_sync(0xffffffffu, pn.y, ks >> 1);
+        const float nl = (ks & 1) ? nly : nlx;                                 // |l*|^2
+        const float ng = __shfl_sync(0xffffffffu, (KT & 1) ? pn.y : pn.x, KT >> 1);   // |g|^2
         float d2g = fmaf(-2.f * s_l, fg, fn2 + ng), d2l = fmaf(-2.f * s_l, fl, fn2 + nl);
         float sg = fmaf(-s_l, fg, fn2), sl = fmaf(-s_l, fl, fn2);              // <fn, fn-g>, <fn, fn-l*>
         const bool row_on = lane < bn && valid;
@@ -707,15 +681,15 @@ energy_tile_kernel(const float* __restrict__ f, const int* __restrict__ perm, co
 #pragma unroll
         for (int r = 0; r < R; ++r) kr[r] = __shfl_sync(0xffffffffu, ks, r);
         if (__any_sync(0xffffffffu, small)) {
-            // ---- exact pass (fn = s f): ||g-fn||^2, ||l*-fn||^2, <f, g-fn>, <f, l*-fn> summed directly, by the group holding l* ----
+            // ---- exact pass (fn = s f): ||g-fn||^2, ||l*-fn||^2, <f, g-fn>, <f, l*-fn> summed directly ----
             float2 w2[S2];
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 float2 aG = make_float2(0.f, 0.f), aL = aG, bG = aG, bL = aG;
                 const float nsr = -__shfl_sync(0xffffffffu, s_l, r);
-                if (r < bn && valid && (NG == 1 || kr[r] / KH == grp)) {
+                if (r < bn && valid) {
                     const float2 m = make_float2(nsr, nsr);
-                    with_proto<KH, 0, KH>(l8, kr[r] - k0, [&](const float4 (&p)[PK_CH]) {
+                    with_proto<KT, 0, KT>(l8, kr[r], [&](const float4 (&p)[PK_CH]) {
 #pragma unroll
                         for (int ch = 0; ch < PK_CH; ++ch) {
                             const float2 x0 = lo2(xv[r][ch]), x1 = hi2(xv[r][ch]);
@@ -729,14 +703,14 @@ energy_tile_kernel(const float* __restrict__ f, const int* __restrict__ perm, co
                 w2[2 * r] = make_float2(aG.x + aG.y, aL.x + aL.y);
                 w2[2 * r + 1] = make_float2(bG.x + bG.y, bL.x + bL.y);
             }
-            const float2 te = tr_reduce<S2>(w2, tr, lane);
-            if (lane % TrCfg<S2>::LPS == 0 && lane / TrCfg<S2>::LPS < S2) cross2[warp * 32 + lane / TrCfg<S2>::LPS] = te;
+            const float2 t = tr_reduce<S2>(w2, tr, lane);
+            if (lane % TrCfg<S2>::LPS == 0 && lane / TrCfg<S2>::LPS < S2) cross2[warp * 32 + lane / TrCfg<S2>::LPS] = t;
             __syncthreads();
             float2 tot2 = make_float2(0.f, 0.f);
             if (lane < S2) {
                 tot2 = cross2[lane];
 #pragma unroll
-                for (int w = 1; w < NW; ++w) tot2 = fadd2(tot2, cross2[w * 32 + lane]);
+                for (int w = 1; w < PK_WARPS; ++w) tot2 = fadd2(tot2, cross2[w * 32 + lane]);
             }
             d2g = __shfl_sync(0xffffffffu, tot2.x, 2 * my_r); d2l = __shfl_sync(0xffffffffu, tot2.y, 2 * my_r);
             sg = -s_l * __shfl_sync(0xffffffffu, tot2.x, 2 * my_r + 1); sl = -s_l * __shfl_sync(0xffffffffu, tot2.y, 2 * my_r + 1);
@@ -755,17 +729,17 @@ energy_tile_kernel(const float* __restrict__ f, const int* __restrict__ perm, co
             per_sample[2 * orig_l + 1] = valid ? dl : bad;
             kstar_out[orig_l] = valid ? ks : 0;
         }
-        // ---- pass 3: gradient rows, written at the samples' original positions by the group that holds l* ----
+        // ---- pass 3: gradient rows, written at the samples' original positions ----
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const float A = __shfl_sync(0xffffffffu, A_l, r), Bg = __shfl_sync(0xffffffffu, Bg_l, r);
             const float Bl = __shfl_sync(0xffffffffu, Bl_l, r);
             const int orig = __shfl_sync(0xffffffffu, orig_l, r);
-            if (r < bn && (NG == 1 || (valid ? kr[r] / KH : r % NG) == grp)) {
+            if (r < bn) {
                 float4* orow = reinterpret_cast<float4*>(grad_f + (size_t)(unsigned)orig * (unsigned)D);
                 if (valid) {
                     const float2 a2 = make_float2(A, A), bg2 = make_float2(Bg, Bg), bl2 = make_float2(Bl, Bl);
-                    with_proto<KH, 0, KH>(l8, kr[r] - k0, [&](const float4 (&p)[PK_CH]) {
+                    with_proto<KT, 0, KT>(l8, kr[r], [&](const float4 (&p)[PK_CH]) {
 #pragma unroll
                         for (int ch = 0; ch < PK_CH; ++ch) {
                             float2 o0 = fmul2(lo2(xv[r][ch]), a2), o1 = fmul2(hi2(xv[r][ch]), a2);
@@ -804,7 +778,7 @@ energy_tile_kernel(const float* __restrict__ f, const int* __restrict__ perm, co
     __syncthreads();
     if (is_last) {
         __threadfence();
-        final_mean<THREADS>(per_sample, B, gs, ls, fin, score);
+        final_mean<EN_THREADS>(per_sample, B, gs, ls, fin, score);
     }
 }
 
@@ -1295,7 +1269,7 @@ static int launch_energy_tile(const float* f, const int64_t* target, const float
     auto kern = full ? energy_tile_kernel<KT, true> : energy_tile_kernel<KT, false>;
     int G = Cfg::CTAS_PER_SM * sm_count();
     if (G > (B + Cfg::R - 1) / Cfg::R) G = (B + Cfg::R - 1) / Cfg::R;
-    return launch_pdl(kern, G, Cfg::THREADS, smem, st, f, (const int*)(ws + w.perm_off), (const int*)(ws + w.off_off), g, l, B, D, C, K, gs,
+    return launch_pdl(kern, G, EN_THREADS, smem, st, f, (const int*)(ws + w.perm_off), (const int*)(ws + w.off_off), g, l, B, D, C, K, gs,
                       ls, normalize_f, score, per_sample, kstar, grad_f, (unsigned int*)(ws + w.ticket_off), stages);
 }
 

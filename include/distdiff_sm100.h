@@ -86,7 +86,11 @@ int dd_add_noise(const void* x, const void* noise, int64_t n, int dtype, float a
  * fp32 arithmetic in ATen's operation order (source coordinate (in/out)*(dst+0.5)-0.5, A = -0.75, taps
  * clamped to the image, rows interpolated along x first, then y), one rounding to the storage type.
  * The backward is a gather with a fixed summation order (ATen scatters with atomics): bit-reproducible.
- * Any scale whose per-tile region fits shared memory (down-scaling up to ~6x, up-scaling up to ~10x). */
+ * Any scale whose per-tile region fits shared memory (down-scaling up to ~6x, up-scaling up to ~10x).
+ * Staging: the forward (all storage types) and the fp32 backward load their input tile as one tensor-map box
+ * (cp.async.bulk.tensor) when the buffer is 16-byte aligned with a row pitch that is a multiple of 16 bytes, planes <= 65535
+ * and the driver exports cuTensorMapEncodeTiled; otherwise -- and for the 16-bit backward -- with plain vector loads.  Both
+ * give the same bits. */
 int dd_bicubic_resize_fwd(const void* in, int64_t planes, int Hin, int Win, int Hout, int Wout, int dtype, void* out,
                           dd_stream_t stream);
 int dd_bicubic_resize_bwd(const void* grad_out, int64_t planes, int Hin, int Win, int Hout, int Wout, int dtype,

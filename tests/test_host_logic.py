@@ -187,3 +187,35 @@ def test_cli_surface_matches_reference_flags():
     assert b.guidance_type == "transform_guidance" and b.K == 5 and b.optimize_targets == "global_prototype-local_prototype"
     with pytest.raises(SystemExit):
         gd.parse_args(["--guidance_type", "not_a_mode"])
+
+
+def test_gpu_decode_loader_logic_on_cpu(tmp_path):
+    """prototypes.GpuDecodeLoader (the opt-in --gpu_decode loader) run with device='cpu': torchvision decodes on the host
+    then, but the batching, the JPEG sniffing, the per-file PIL fallback (a PNG) and the resize / normalise arithmetic are the
+    same code.  Against the reference's PIL transform (dataloader.py:736-742) the tensors agree to a few grey levels."""
+    import numpy as np
+    import torch
+    from PIL import Image
+    from torchvision import transforms
+    from distdiff_b200 import data as dd_data, prototypes
+    syn = dd_data.SyntheticCaltech(2, 5, hw=(120, 160))
+    root = tmp_path / "train"
+    for i in range(len(syn)):
+        d = root / syn.class_names[syn.targets[i]].replace(" ", "_")
+        d.mkdir(parents=True, exist_ok=True)
+        img = syn.image(i).resize((160 + 3 * i, 120 + 5 * (i % 3)), Image.BICUBIC)
+        img.save(d / (f"image_{i:04d}.png" if i == 2 else f"image_{i:04d}.jpg"), quality=95)
+    tf = transforms.Compose([transforms.Resize((224, 224)), transforms.ToTensor(),
+                             transforms.Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])])
+    base = dd_data.ImageFolderSorted(str(root), tf)
+    idx = list(range(len(base)))
+    loader = prototypes.GpuDecodeLoader([base.paths[i] for i in idx], [base.targets[i] for i in idx], torch.device("cpu"), batch_size=4,
+                                        fallback=base, fallback_index=idx, transform=tf)
+    xs, ys = zip(*list(loader))
+    x = torch.cat(xs); y = torch.cat(ys)
+    assert len(xs) == len(loader) == 3 and x.shape == (10, 3, 224, 224) and y.tolist() == base.targets
+    assert loader.decoded_on_gpu == 9                                        # everything but the PNG
+    ref = torch.stack([base[i][0] for i in idx])
+    assert torch.equal(x[2], ref[2])                                         # the PNG went through the reference's own path
+    err = (x - ref).abs() * 0.226 * 255                                      # back to grey levels (std ~0.226)
+    assert float(err.max()) <= 6.0 and float(err.mean()) <= 0.6
